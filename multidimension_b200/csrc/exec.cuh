@@ -1,0 +1,672 @@
+// exec.cuh — per-thread evaluator of a lowered View chain (device code).
+//
+// One thread computes V consecutive output elements along the innermost output axis ("a
+// vector").  The op tree is a postfix program over a small value stack held in REGISTERS:
+// every function here is force-inlined into a context where the stack depth D is a compile-time
+// constant, so `st[D][lane]` never needs dynamic indexing.  Two drivers use it:
+//   * run_static<Sig,...>  — the instruction stream (opcode,dtype,op,aux) is a compile-time
+//     signature; the compiler folds every switch away.  This is the device-side analogue of the
+//     reference's monomorphisation of `Zip<Map<..>>` types into one `collect` loop.
+//   * run_interp<...>      — `switch (depth)` into the same code with run-time opcodes, for any
+//     chain without a pre-instantiated signature.
+//
+// When compiled without __CUDACC__ (tests/emu only) the same source runs on the host, one
+// "thread" at a time, so planner + evaluator logic can be checked against the oracle on a box
+// without a GPU.  That build is test infrastructure and is never linked into the product.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include "program.hpp"
+
+#if defined(__CUDACC__)
+#define MDIM_FN __device__ __forceinline__
+#else
+#include <math.h>
+#define MDIM_FN static inline __attribute__((always_inline))
+#endif
+
+namespace mdim {
+
+// ------------------------------------------------------------------------------------------------
+// scalar helpers
+// ------------------------------------------------------------------------------------------------
+MDIM_FN float as_f32(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+MDIM_FN uint32_t f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+MDIM_FN double as_f64(uint64_t u) { double f; memcpy(&f, &u, 8); return f; }
+MDIM_FN uint64_t f64_bits(double f) { uint64_t u; memcpy(&u, &f, 8); return u; }
+
+// Rust never contracts `x*y+1.0` into an FMA and rounds every operation separately
+// (SURVEY.md §7 hard part 7): use the explicit round-to-nearest intrinsics, which nvcc never fuses.
+#if defined(__CUDA_ARCH__)
+MDIM_FN float f_add(float a, float b) { return __fadd_rn(a, b); }
+MDIM_FN float f_sub(float a, float b) { return __fsub_rn(a, b); }
+MDIM_FN float f_mul(float a, float b) { return __fmul_rn(a, b); }
+MDIM_FN float f_div(float a, float b) { return __fdiv_rn(a, b); }
+MDIM_FN double d_add(double a, double b) { return __dadd_rn(a, b); }
+MDIM_FN double d_sub(double a, double b) { return __dsub_rn(a, b); }
+MDIM_FN double d_mul(double a, double b) { return __dmul_rn(a, b); }
+MDIM_FN double d_div(double a, double b) { return __ddiv_rn(a, b); }
+#else
+MDIM_FN float f_add(float a, float b) { volatile float r = a + b; return r; }
+MDIM_FN float f_sub(float a, float b) { volatile float r = a - b; return r; }
+MDIM_FN float f_mul(float a, float b) { volatile float r = a * b; return r; }
+MDIM_FN float f_div(float a, float b) { volatile float r = a / b; return r; }
+MDIM_FN double d_add(double a, double b) { volatile double r = a + b; return r; }
+MDIM_FN double d_sub(double a, double b) { volatile double r = a - b; return r; }
+MDIM_FN double d_mul(double a, double b) { volatile double r = a * b; return r; }
+MDIM_FN double d_div(double a, double b) { volatile double r = a / b; return r; }
+#endif
+
+MDIM_FN int esize_of(int dt) { return dt == MDIM_U8 ? 1 : (dt == MDIM_I32 || dt == MDIM_U32 || dt == MDIM_F32) ? 4 : 8; }
+
+// ------------------------------------------------------------------------------------------------
+// global memory access.  Streaming vector loads bypass L1 (read once); scalar broadcast / strided /
+// gather loads go through L1 (re-used across lanes and neighbouring threads).
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+MDIM_FN void ld128_stream(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+}
+MDIM_FN void ld64_stream(const void* p, uint32_t& a, uint32_t& b) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+}
+MDIM_FN uint32_t ld32_stream(const void* p) {
+    uint32_t a; asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(a) : "l"(p)); return a;
+}
+MDIM_FN uint32_t ld32(const void* p) { return __ldg((const uint32_t*)p); }
+MDIM_FN uint64_t ld64(const void* p) { return __ldg((const unsigned long long*)p); }
+MDIM_FN uint32_t ld8(const void* p) { return __ldg((const uint8_t*)p); }
+MDIM_FN void st128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool cs) {
+    if (cs) asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+    else asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+MDIM_FN void st64(void* p, uint32_t a, uint32_t b) {
+    asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+MDIM_FN void st32(void* p, uint32_t a) { *(uint32_t*)p = a; }
+MDIM_FN void st8(void* p, uint32_t a) { *(uint8_t*)p = (uint8_t)a; }
+MDIM_FN void err_min(unsigned long long* p, unsigned long long v) { atomicMin(p, v); }
+#else
+MDIM_FN void ld128_stream(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    const uint32_t* q = (const uint32_t*)p; a = q[0]; b = q[1]; c = q[2]; d = q[3];
+}
+MDIM_FN void ld64_stream(const void* p, uint32_t& a, uint32_t& b) { const uint32_t* q = (const uint32_t*)p; a = q[0]; b = q[1]; }
+MDIM_FN uint32_t ld32_stream(const void* p) { return *(const uint32_t*)p; }
+MDIM_FN uint32_t ld32(const void* p) { return *(const uint32_t*)p; }
+MDIM_FN uint64_t ld64(const void* p) { return *(const uint64_t*)p; }
+MDIM_FN uint32_t ld8(const void* p) { return *(const uint8_t*)p; }
+MDIM_FN void st128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool) { uint32_t* q = (uint32_t*)p; q[0] = a; q[1] = b; q[2] = c; q[3] = d; }
+MDIM_FN void st64(void* p, uint32_t a, uint32_t b) { uint32_t* q = (uint32_t*)p; q[0] = a; q[1] = b; }
+MDIM_FN void st32(void* p, uint32_t a) { *(uint32_t*)p = a; }
+MDIM_FN void st8(void* p, uint32_t a) { *(uint8_t*)p = (uint8_t)a; }
+MDIM_FN void err_min(unsigned long long* p, unsigned long long v) { if (v < *p) *p = v; }
+#endif
+
+template <class S> MDIM_FN S ld_scalar(const void* base, int64_t idx, int esize) {
+    if (esize == 4) return (S)ld32((const char*)base + idx * 4);
+    if (esize == 1) return (S)ld8((const char*)base + idx);
+    if (sizeof(S) == 8) return (S)ld64((const char*)base + idx * 8);
+    return 0;
+}
+
+// V consecutive elements starting at element `idx`; the planner guarantees the alignment.
+template <class S, int V> MDIM_FN void ld_vector(const void* base, int64_t idx, int esize, S (&d)[V]) {
+    if (esize == 4) {
+        const char* p = (const char*)base + idx * 4;
+        if constexpr (V % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < V; i += 4) {
+                uint32_t a, b, c, e;
+                ld128_stream(p + i * 4, a, b, c, e);
+                d[i] = a; d[i + 1] = b; d[i + 2] = c; d[i + 3] = e;
+            }
+        } else if constexpr (V == 2) {
+            uint32_t a, b; ld64_stream(p, a, b); d[0] = a; d[1] = b;
+        } else {
+            d[0] = ld32_stream(p);
+        }
+    } else if (esize == 8) {
+        if constexpr (sizeof(S) == 8) {
+            const char* p = (const char*)base + idx * 8;
+            if constexpr (V % 2 == 0) {
+#pragma unroll
+                for (int i = 0; i < V; i += 2) {
+                    uint32_t a, b, c, e;
+                    ld128_stream(p + i * 8, a, b, c, e);
+                    d[i] = (S)a | ((S)b << 32); d[i + 1] = (S)c | ((S)e << 32);
+                }
+            } else {
+                uint32_t a, b; ld64_stream(p, a, b); d[0] = (S)a | ((S)b << 32);
+            }
+        }
+    } else {
+        const char* p = (const char*)base + idx;
+        if constexpr (V == 8) {
+            uint32_t a, b; ld64_stream(p, a, b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { d[i] = (a >> (8 * i)) & 0xffu; d[4 + i] = (b >> (8 * i)) & 0xffu; }
+        } else if constexpr (V == 4) {
+            uint32_t a = ld32_stream(p);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = (a >> (8 * i)) & 0xffu;
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) d[i] = (S)ld8(p + i);
+        }
+    }
+}
+
+template <class S, int V> MDIM_FN void st_vector(void* base, uint64_t idx, int esize, const S (&d)[V], bool cs) {
+    if (esize == 4) {
+        char* p = (char*)base + idx * 4;
+        if constexpr (V % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < V; i += 4) st128(p + i * 4, (uint32_t)d[i], (uint32_t)d[i + 1], (uint32_t)d[i + 2], (uint32_t)d[i + 3], cs);
+        } else if constexpr (V == 2) {
+            st64(p, (uint32_t)d[0], (uint32_t)d[1]);
+        } else {
+            st32(p, (uint32_t)d[0]);
+        }
+    } else if (esize == 8) {
+        if constexpr (sizeof(S) == 8) {
+            char* p = (char*)base + idx * 8;
+            if constexpr (V % 2 == 0) {
+#pragma unroll
+                for (int i = 0; i < V; i += 2)
+                    st128(p + i * 8, (uint32_t)d[i], (uint32_t)(d[i] >> 32), (uint32_t)d[i + 1], (uint32_t)(d[i + 1] >> 32), cs);
+            } else {
+                st64(p, (uint32_t)d[0], (uint32_t)(d[0] >> 32));
+            }
+        }
+    } else {
+        char* p = (char*)base + idx;
+        if constexpr (V == 8) {
+            uint32_t a = 0, b = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a |= ((uint32_t)d[i] & 0xffu) << (8 * i); b |= ((uint32_t)d[4 + i] & 0xffu) << (8 * i); }
+            st64(p, a, b);
+        } else if constexpr (V == 4) {
+            uint32_t a = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a |= ((uint32_t)d[i] & 0xffu) << (8 * i);
+            st32(p, a);
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) st8(p + i, (uint32_t)d[i]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// value semantics.  A slot holds the raw bits of one value, zero-extended to the slot width.
+// Integer semantics follow Rust RELEASE builds: add/sub/mul wrap, shift amounts are masked,
+// x/0 and MIN/-1 panic in every build mode (→ arith error).  Floats are IEEE, never fused.
+// ------------------------------------------------------------------------------------------------
+template <class S> MDIM_FN S bin_op(int dt, int op, int rdt, S a, S b, bool& arith) {
+    if (dt == MDIM_F32) {
+        float x = as_f32((uint32_t)a), y = as_f32((uint32_t)b), r = 0.f;
+        switch (op) {
+            case MDIM_ADD: r = f_add(x, y); break;
+            case MDIM_SUB: r = f_sub(x, y); break;
+            case MDIM_MUL: r = f_mul(x, y); break;
+            case MDIM_DIV: r = f_div(x, y); break;
+            case MDIM_REM: r = fmodf(x, y); break;  // Rust f32 % is fmod, exact
+        }
+        return (S)f32_bits(r);
+    }
+    if (dt == MDIM_I32 || dt == MDIM_U32 || dt == MDIM_U8) {
+        uint32_t x = (uint32_t)a, y = (uint32_t)b, r = 0;
+        const uint32_t bits = dt == MDIM_U8 ? 8u : 32u;
+        switch (op) {
+            case MDIM_ADD: r = x + y; break;
+            case MDIM_SUB: r = x - y; break;
+            case MDIM_MUL: r = x * y; break;
+            case MDIM_AND: r = x & y; break;
+            case MDIM_OR: r = x | y; break;
+            case MDIM_XOR: r = x ^ y; break;
+            case MDIM_SHL: r = x << ((uint32_t)b & (bits - 1)); break;  // low bits of any rhs dtype
+            case MDIM_SHR:
+                r = dt == MDIM_I32 ? (uint32_t)((int32_t)x >> ((uint32_t)b & 31u)) : x >> ((uint32_t)b & (bits - 1));
+                break;
+            case MDIM_DIV:
+            case MDIM_REM:
+                if (y == 0 || (dt == MDIM_I32 && x == 0x80000000u && y == 0xffffffffu)) { arith = true; r = 0; }
+                else if (dt == MDIM_I32) r = op == MDIM_DIV ? (uint32_t)((int32_t)x / (int32_t)y) : (uint32_t)((int32_t)x % (int32_t)y);
+                else r = op == MDIM_DIV ? x / y : x % y;
+                break;
+        }
+        if (dt == MDIM_U8) r &= 0xffu;
+        (void)rdt;
+        return (S)r;
+    }
+    if constexpr (sizeof(S) == 8) {
+        if (dt == MDIM_F64) {
+            double x = as_f64(a), y = as_f64(b), r = 0.;
+            switch (op) {
+                case MDIM_ADD: r = d_add(x, y); break;
+                case MDIM_SUB: r = d_sub(x, y); break;
+                case MDIM_MUL: r = d_mul(x, y); break;
+                case MDIM_DIV: r = d_div(x, y); break;
+                case MDIM_REM: r = fmod(x, y); break;
+            }
+            return f64_bits(r);
+        }
+        uint64_t x = a, y = b, r = 0;
+        switch (op) {
+            case MDIM_ADD: r = x + y; break;
+            case MDIM_SUB: r = x - y; break;
+            case MDIM_MUL: r = x * y; break;
+            case MDIM_AND: r = x & y; break;
+            case MDIM_OR: r = x | y; break;
+            case MDIM_XOR: r = x ^ y; break;
+            case MDIM_SHL: r = x << (y & 63u); break;
+            case MDIM_SHR: r = dt == MDIM_I64 ? (uint64_t)((int64_t)x >> (y & 63u)) : x >> (y & 63u); break;
+            case MDIM_DIV:
+            case MDIM_REM:
+                if (y == 0 || (dt == MDIM_I64 && x == 0x8000000000000000ull && y == ~0ull)) { arith = true; r = 0; }
+                else if (dt == MDIM_I64) r = op == MDIM_DIV ? (uint64_t)((int64_t)x / (int64_t)y) : (uint64_t)((int64_t)x % (int64_t)y);
+                else r = op == MDIM_DIV ? x / y : x % y;
+                break;
+        }
+        return r;
+    }
+    return 0;
+}
+
+// Rust `as`: float→int saturates and maps NaN to 0; int→int truncates / sign-extends;
+// int→float rounds to nearest even.
+MDIM_FN int64_t sat_i64(double f, int64_t lo, int64_t hi) {
+    if (f != f) return 0;
+    if (f <= (double)lo) return lo;
+    if (f >= (double)hi) return hi;
+    return (int64_t)f;
+}
+MDIM_FN uint64_t sat_u64(double f, uint64_t hi) {
+    if (f != f || f <= 0.0) return 0;
+    if (f >= (double)hi) return hi;
+    return (uint64_t)f;
+}
+
+template <class S> MDIM_FN S cast_val(int from, int to, S a) {
+    if (from == to) return a;
+    const bool from_f = from == MDIM_F32 || from == MDIM_F64;
+    if (from_f) {
+        double d;
+        if (from == MDIM_F32) d = (double)as_f32((uint32_t)a);
+        else { if constexpr (sizeof(S) == 8) d = as_f64(a); else d = 0.; }
+        switch (to) {
+            case MDIM_U8: return (S)sat_u64(d, 255);
+            case MDIM_I32: return (S)(uint32_t)(int32_t)sat_i64(d, INT32_MIN, INT32_MAX);
+            case MDIM_U32: return (S)sat_u64(d, 0xffffffffull);
+            case MDIM_I64: return (S)(uint64_t)sat_i64(d, INT64_MIN, INT64_MAX);
+            case MDIM_U64: return (S)sat_u64(d, ~0ull);
+            case MDIM_F32: return (S)f32_bits((float)d);
+            case MDIM_F64: if constexpr (sizeof(S) == 8) return f64_bits(d); else return 0;
+        }
+        return 0;
+    }
+    // integer source: canonical 64-bit two's complement value
+    uint64_t bits;
+    bool sgn = false;
+    switch (from) {
+        case MDIM_I32: bits = (uint64_t)(int64_t)(int32_t)(uint32_t)a; sgn = true; break;
+        case MDIM_I64: bits = (uint64_t)a; sgn = true; break;
+        default: bits = (uint64_t)a; break;
+    }
+    switch (to) {
+        case MDIM_U8: return (S)(bits & 0xffu);
+        case MDIM_I32: case MDIM_U32: return (S)(uint32_t)bits;
+        case MDIM_I64: case MDIM_U64: return (S)bits;
+        case MDIM_F32: return (S)f32_bits(sgn ? (float)(int64_t)bits : (float)bits);
+        case MDIM_F64: if constexpr (sizeof(S) == 8) return f64_bits(sgn ? (double)(int64_t)bits : (double)bits); else return 0;
+    }
+    return 0;
+}
+
+template <class S> MDIM_FN S un_op(int op, int dt, int src_dt, S a) {
+    if (op == MDIM_CAST) return cast_val<S>(src_dt, dt, a);
+    if (dt == MDIM_F32) {
+        float x = as_f32((uint32_t)a);
+        switch (op) {
+            case MDIM_NEG: return (S)(f32_bits(x) ^ 0x80000000u);
+            case MDIM_ABS: return (S)(f32_bits(x) & 0x7fffffffu);
+            case MDIM_SQRT: return (S)f32_bits(sqrtf(x));
+        }
+        return a;
+    }
+    if (dt == MDIM_F64) {
+        if constexpr (sizeof(S) == 8) {
+            switch (op) {
+                case MDIM_NEG: return a ^ 0x8000000000000000ull;
+                case MDIM_ABS: return a & 0x7fffffffffffffffull;
+                case MDIM_SQRT: return f64_bits(sqrt(as_f64(a)));
+            }
+        }
+        return a;
+    }
+    if (dt == MDIM_I64 || dt == MDIM_U64) {
+        if constexpr (sizeof(S) == 8) {
+            switch (op) {
+                case MDIM_NEG: return (S)(0ull - a);
+                case MDIM_NOT: return (S)~a;
+                case MDIM_ABS: return (dt == MDIM_I64 && (int64_t)a < 0) ? (S)(0ull - a) : a;
+            }
+        }
+        return a;
+    }
+    uint32_t x = (uint32_t)a, r = x;
+    switch (op) {
+        case MDIM_NEG: r = 0u - x; break;
+        case MDIM_NOT: r = ~x; break;
+        case MDIM_ABS: r = (dt == MDIM_I32 && (int32_t)x < 0) ? 0u - x : x; break;
+    }
+    if (dt == MDIM_U8) r &= 0xffu;
+    return (S)r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-thread state
+// ------------------------------------------------------------------------------------------------
+template <bool WIDE> struct CoordTraits { using coord_t = uint32_t; using stride_t = int32_t; };
+template <> struct CoordTraits<true> { using coord_t = uint64_t; using stride_t = int64_t; };
+
+template <bool WIDE> struct ThreadState {
+    typename CoordTraits<WIDE>::coord_t c[kMaxRank];  // element coordinates of lane 0
+    uint64_t pos0;                                    // linear output position of lane 0
+    uint64_t red_k;                                   // reduction step counter
+    uint32_t mask;                                    // lane-active mask (Diagonal laziness)
+};
+
+template <bool WIDE> MDIM_FN int64_t addr_offset(const Program& P, int slot, const ThreadState<WIDE>& ts) {
+    using stride_t = typename CoordTraits<WIDE>::stride_t;
+    int64_t off = P.addr[slot].offset;
+    const int naxes = P.rank + P.red_rank;
+#pragma unroll
+    for (int a = 0; a < kMaxRank; ++a)
+        if (a < naxes) off += (int64_t)(stride_t)ts.c[a] * (int64_t)(stride_t)P.addr[slot].stride[a];
+    return off;
+}
+
+template <bool WIDE> MDIM_FN int64_t inner_stride(const Program& P, int slot) {
+    return P.rank > 0 ? P.addr[slot].stride[P.rank - 1] : 0;
+}
+
+// coordinate of `axis` for lane `lane` (only the innermost output axis varies across lanes)
+template <bool WIDE> MDIM_FN uint64_t lane_coord(const Program& P, const ThreadState<WIDE>& ts, int axis, int lane) {
+    // mask arithmetic rather than `if (a == axis) v = c[a]`: the compiler turns the latter back
+    // into a dynamically indexed load, which forces the coordinates into local memory
+    uint64_t v = 0;
+#pragma unroll
+    for (int a = 0; a < kMaxRank; ++a) v |= (uint64_t)ts.c[a] & (0ull - (uint64_t)(a == axis));
+    return axis == P.rank - 1 ? v + (uint64_t)lane : v;
+}
+
+template <int V, bool WIDE> MDIM_FN uint32_t eval_preds(const Program& P, const ThreadState<WIDE>& ts, int first, int n) {
+    uint32_t m = (1u << V) - 1u;
+    for (int p = first; p < first + n; ++p) {
+        const int a = P.pred[p].a, b = P.pred[p].b;
+#pragma unroll
+        for (int l = 0; l < V; ++l) {
+            const uint64_t lhs = lane_coord<WIDE>(P, ts, a, l);
+            const uint64_t rhs = b >= 0 ? lane_coord<WIDE>(P, ts, b, l) : P.pred[p].c;
+            if (lhs != rhs) m &= ~(1u << l);
+        }
+    }
+    return m;
+}
+
+MDIM_FN void report(const Program& P, ErrWord* err, uint64_t pos, int status, int node, int comp, uint64_t value, uint64_t bound) {
+    err_min(&err->pos, (unsigned long long)pos);
+    if ((P.flags & PF_EXPLAIN) && pos == P.explain_pos && err->status == 0) {
+        err->status = status; err->node = node; err->component = comp;
+        err->value = value; err->bound = bound;
+    }
+}
+
+// depth change of one instruction
+MDIM_FN int depth_delta(int opc, int aux) {
+    switch (opc) {
+        case OPC_LEAF_VEC: case OPC_LEAF_BCAST: case OPC_LEAF_STRIDED: case OPC_IOTA: case OPC_CONST: case OPC_FOLD_BEGIN: return 1;
+        case OPC_BINARY: case OPC_FOLD_STEP: return -1;
+        case OPC_GATHER: return 1 - aux;
+        default: return 0;
+    }
+}
+
+// GATHER with NC index components at st[D-NC .. D-1]; result replaces st[D-NC].
+// Compose::at = w.at(v.at(i)) (src/view.rs:905,911); each component is bounds-checked like
+// usize::to_usize (src/int.rs:16-19) in component order; inactive (off-diagonal) lanes neither
+// load nor report, because Diagonal::at never evaluates its inner view there (src/view.rs:854-856).
+template <int D, int NC, class S, int V, int MAXD, bool WIDE>
+MDIM_FN void exec_gather(const Program& P, ErrWord* err, const Instr& I, S (&st)[MAXD][V], const ThreadState<WIDE>& ts) {
+    if constexpr (sizeof(S) == 8 && D >= NC && NC >= 1) {
+        const Addr& A = P.addr[I.slot];
+        const int64_t base = addr_offset<WIDE>(P, I.slot, ts);
+        const int64_t s_in = inner_stride<WIDE>(P, I.slot);
+        const int es = esize_of(I.dtype);
+#pragma unroll
+        for (int l = 0; l < V; ++l) {
+            int64_t idx = base + (int64_t)l * s_in;
+            bool ok = (ts.mask >> l) & 1u;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const uint64_t k = (uint64_t)st[D - NC + c][l];
+                if (ok && !(k < A.bound[c])) {
+                    report(P, err, ts.pos0 + l, MDIM_ERR_OOB, I.n, c, k, A.bound[c]);
+                    ok = false;
+                }
+                idx += (int64_t)k * A.gstride[c];
+            }
+            S v = 0;
+            if (ok) {
+                if (A.n_peers > 1) {
+                    const uint64_t p = (uint64_t)idx / P.peers.block;
+                    v = ld_scalar<S>(P.peers.peer[p], (int64_t)((uint64_t)idx - p * P.peers.block), es);
+                } else {
+                    v = ld_scalar<S>(A.ptr, idx, es);
+                }
+            }
+            st[D - NC][l] = v;
+        }
+    }
+}
+
+// Execute instruction I at compile-time stack depth D.  Returns the next pc.
+template <int D, class S, int V, int MAXD, bool WIDE>
+MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int op, int aux, int pc,
+                       S (&st)[MAXD][V], ThreadState<WIDE>& ts) {
+    const Instr& I = P.instr[pc];
+    int next = pc + 1;
+    switch (opc) {
+        case OPC_LEAF_VEC:  // Array::at = items[to_usize(index)] (src/array.rs:81,86), V at a time
+            if constexpr (D < MAXD) ld_vector<S, V>(P.addr[I.slot].ptr, addr_offset<WIDE>(P, I.slot, ts), esize_of(dtype), st[D]);
+            break;
+        case OPC_LEAF_BCAST:  // operand lacks the vector axis: Broadcast::index drops it (src/broadcast.rs:46-60)
+            if constexpr (D < MAXD) {
+                const S v = ld_scalar<S>(P.addr[I.slot].ptr, addr_offset<WIDE>(P, I.slot, ts), esize_of(dtype));
+#pragma unroll
+                for (int l = 0; l < V; ++l) st[D][l] = v;
+            }
+            break;
+        case OPC_LEAF_STRIDED:
+            if constexpr (D < MAXD) {
+                const int64_t off = addr_offset<WIDE>(P, I.slot, ts), s_in = inner_stride<WIDE>(P, I.slot);
+                const int es = esize_of(dtype);
+#pragma unroll
+                for (int l = 0; l < V; ++l) st[D][l] = ld_scalar<S>(P.addr[I.slot].ptr, off + (int64_t)l * s_in, es);
+            }
+            break;
+        case OPC_IOTA:  // All<I>::at(index) = index (src/index.rs:185)
+            if constexpr (D < MAXD) {
+                const int64_t off = addr_offset<WIDE>(P, I.slot, ts), s_in = inner_stride<WIDE>(P, I.slot);
+#pragma unroll
+                for (int l = 0; l < V; ++l) {
+                    const uint64_t x = (uint64_t)(off + (int64_t)l * s_in);
+                    if constexpr (sizeof(S) == 8) st[D][l] = cast_val<S>(MDIM_U64, dtype, x);
+                    else st[D][l] = dtype == MDIM_F32 ? (S)f32_bits((float)x) : dtype == MDIM_U8 ? (S)(x & 0xffu) : (S)(uint32_t)x;
+                }
+            }
+            break;
+        case OPC_CONST:  // Scalar::at (src/view.rs:1407)
+            if constexpr (D < MAXD) {
+#pragma unroll
+                for (int l = 0; l < V; ++l) st[D][l] = (S)I.imm;
+            }
+            break;
+        case OPC_UNARY:  // Map::at = f(v.at(i)) (src/view.rs:888), closed op set
+            if constexpr (D >= 1) {
+#pragma unroll
+                for (int l = 0; l < V; ++l) st[D - 1][l] = un_op<S>(op, dtype, aux, st[D - 1][l]);
+            }
+            break;
+        case OPC_BINARY:  // Zip::at = B::call(v.at(vi), w.at(wi)) (src/view.rs:1194-1197)
+            if constexpr (D >= 2) {
+#pragma unroll
+                for (int l = 0; l < V; ++l) {
+                    bool arith = false;
+                    st[D - 2][l] = bin_op<S>(dtype, op, aux, st[D - 2][l], st[D - 1][l], arith);
+                    if (arith && ((ts.mask >> l) & 1u)) report(P, err, ts.pos0 + l, MDIM_ERR_ARITH, I.n, 0, (uint64_t)st[D - 1][l], 0);
+                }
+            }
+            break;
+        case OPC_MASK:
+            ts.mask = I.n ? eval_preds<V, WIDE>(P, ts, I.slot, I.n) : ((1u << V) - 1u);
+            break;
+        case OPC_SELECT:  // Diagonal::at (src/view.rs:854-856)
+            if constexpr (D >= 1) {
+                const uint32_t m = eval_preds<V, WIDE>(P, ts, I.slot, I.n);
+#pragma unroll
+                for (int l = 0; l < V; ++l) st[D - 1][l] = ((m >> l) & 1u) ? st[D - 1][l] : (S)I.imm;
+            }
+            break;
+        case OPC_GATHER:
+            if (aux == 1) exec_gather<D, 1, S, V, MAXD, WIDE>(P, err, I, st, ts);
+            else if (aux == 2) exec_gather<D, 2, S, V, MAXD, WIDE>(P, err, I, st, ts);
+            else if (aux == 3) exec_gather<D, 3, S, V, MAXD, WIDE>(P, err, I, st, ts);
+            break;
+        case OPC_FOLD_BEGIN:  // let mut s = init;  (the closure of rows().map(..))
+            if constexpr (D < MAXD) {
+#pragma unroll
+                for (int l = 0; l < V; ++l) st[D][l] = (S)I.imm;
+#pragma unroll
+                for (int a = 0; a < kMaxRank; ++a)
+                    if (a >= P.rank) ts.c[a] = 0;
+                ts.red_k = 0;
+                if (P.red_count == 0) next = I.slot;  // empty row: skip the body and its FOLD_STEP
+            }
+            break;
+        case OPC_FOLD_STEP:  // row.each(|x| s = s (op) x): sequential, index order (src/view.rs:250-252)
+            if constexpr (D >= 2) {
+#pragma unroll
+                for (int l = 0; l < V; ++l) {
+                    bool arith = false;
+                    st[D - 2][l] = bin_op<S>(dtype, op, aux, st[D - 2][l], st[D - 1][l], arith);
+                    if (arith && ((ts.mask >> l) & 1u)) report(P, err, ts.pos0 + l, MDIM_ERR_ARITH, I.n, 0, (uint64_t)st[D - 1][l], 0);
+                }
+                bool carry = true;  // advance the reduction coordinates, last axis fastest
+#pragma unroll
+                for (int a = kMaxRank - 1; a >= 0; --a) {
+                    if (carry && a >= P.rank && a < P.rank + P.red_rank) {
+                        ts.c[a] += 1;
+                        if ((uint64_t)ts.c[a] == P.length[a]) ts.c[a] = 0; else carry = false;
+                    }
+                }
+                ts.red_k += 1;
+                if (ts.red_k < P.red_count) next = I.slot;
+            }
+            break;
+    }
+    return next;
+}
+
+// ------------------------------------------------------------------------------------------------
+// drivers
+// ------------------------------------------------------------------------------------------------
+// compile-time signature: Sig::n instructions, Sig::code[i] = {opc, dtype, op, aux}
+struct SigInstr { uint8_t opc, dtype, op, aux; };
+
+struct NoSig { static constexpr int n = 0; };
+
+template <class Sig, int PC, int D, class S, int V, int MAXD, bool WIDE>
+MDIM_FN void run_static(const Program& P, ErrWord* err, S (&st)[MAXD][V], ThreadState<WIDE>& ts) {
+    if constexpr (PC < Sig::n) {
+        constexpr SigInstr I = Sig::code[PC];
+        exec_instr<D, S, V, MAXD, WIDE>(P, err, I.opc, I.dtype, I.op, I.aux, PC, st, ts);
+        constexpr int ND = D + (I.opc == OPC_LEAF_VEC || I.opc == OPC_LEAF_BCAST || I.opc == OPC_LEAF_STRIDED || I.opc == OPC_IOTA ||
+                                        I.opc == OPC_CONST ? 1
+                                : I.opc == OPC_BINARY ? -1
+                                : I.opc == OPC_GATHER ? 1 - (int)I.aux
+                                                      : 0);
+        run_static<Sig, PC + 1, ND, S, V, MAXD, WIDE>(P, err, st, ts);
+    }
+}
+
+template <int D, class S, int V, int MAXD, bool WIDE>
+MDIM_FN int interp_step(const Program& P, ErrWord* err, int depth, const Instr& I, int pc, S (&st)[MAXD][V], ThreadState<WIDE>& ts) {
+    if constexpr (D > MAXD) {
+        return P.n_instr;  // unreachable: the planner bounds the depth
+    } else {
+        if (depth == D) return exec_instr<D, S, V, MAXD, WIDE>(P, err, I.opc, I.dtype, I.op, I.aux, pc, st, ts);
+        return interp_step<D + 1, S, V, MAXD, WIDE>(P, err, depth, I, pc, st, ts);
+    }
+}
+
+template <class S, int V, int MAXD, bool WIDE>
+MDIM_FN void run_interp(const Program& P, ErrWord* err, S (&st)[MAXD][V], ThreadState<WIDE>& ts) {
+    int pc = 0, depth = 0;
+    while (pc < P.n_instr) {
+        const Instr& I = P.instr[pc];
+        const int d = depth_delta(I.opc, I.aux);
+        pc = interp_step<0, S, V, MAXD, WIDE>(P, err, depth, I, pc, st, ts);
+        depth += d;
+    }
+}
+
+// Fast unsigned division by a run-time constant for n < 2^31 (planner guarantees the range):
+// q = umulhi(n, mul) >> shr.
+MDIM_FN uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t shr) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(n, mul) >> shr;
+#else
+    return (uint32_t)(((uint64_t)n * mul) >> 32) >> shr;
+#endif
+}
+
+// One output vector: decode (Index::from_usize peels the LAST component first, src/index.rs:116-120,
+// src/lib.rs:38-39), evaluate, store at its to_usize position (row-major, src/index.rs:109-114).
+template <class Sig, class S, int V, int MAXD, bool WIDE, bool R1>
+MDIM_FN void eval_vector(const Program& P, void* out, ErrWord* err, uint64_t g) {
+    using coord_t = typename CoordTraits<WIDE>::coord_t;
+    ThreadState<WIDE> ts;
+    ts.pos0 = g * (uint64_t)V;
+    ts.mask = (1u << V) - 1u;
+    ts.red_k = 0;
+#pragma unroll
+    for (int a = 0; a < kMaxRank; ++a) ts.c[a] = 0;
+    if constexpr (R1) {
+        ts.c[0] = (coord_t)(g * (uint64_t)V);
+    } else {
+        coord_t rem = (coord_t)g;
+#pragma unroll
+        for (int a = kMaxRank - 1; a >= 1; --a) {
+            if (a < P.rank) {
+                const bool inner = (a == P.rank - 1);
+                const uint64_t len = inner ? P.length[a] / (uint64_t)V : P.length[a];
+                coord_t q;
+                if constexpr (WIDE) q = rem / (coord_t)len;
+                else q = fast_div(rem, P.div_mul[a], P.div_shr[a]);
+                const coord_t r = rem - q * (coord_t)len;
+                ts.c[a] = inner ? r * (coord_t)V : r;  // element coordinate of lane 0
+                rem = q;
+            }
+        }
+        ts.c[0] = P.rank <= 1 ? rem * (coord_t)V : rem;
+    }
+    S st[MAXD][V];
+    if constexpr (Sig::n > 0) run_static<Sig, 0, 0, S, V, MAXD, WIDE>(P, err, st, ts);
+    else run_interp<S, V, MAXD, WIDE>(P, err, st, ts);
+    st_vector<S, V>(out, ts.pos0, esize_of(P.out_dtype), st[0], true);
+}
+
+}  // namespace mdim

@@ -1,0 +1,21 @@
+// k_eval_s32.cu — instantiations of the fused evaluator with 32-bit value slots (sm_100a).
+#include "kernels.cuh"
+#include "sigs.hpp"
+
+namespace mdim {
+
+template <class Sig> constexpr const SigInstr* sig_code() { if constexpr (Sig::n > 0) return Sig::code; else return nullptr; }
+
+static const EvalVariant kVariants[] = {
+#define X(Sig, S, V, MAXD, WIDE, R1) \
+    {#Sig, (int)sizeof(S), V, MAXD, WIDE ? 1 : 0, R1 ? 1 : 0, sig_code<Sig>(), Sig::n, &k_eval<Sig, S, V, MAXD, WIDE, R1>},
+#include "variants_s32.inc"
+#undef X
+};
+
+const EvalVariant* eval_variants_s32(int* n) {
+    *n = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+    return kVariants;
+}
+
+}  // namespace mdim

@@ -1,0 +1,142 @@
+// k_transpose.cu — K2: batched tiled transpose of one leaf through swizzled shared memory (sm_100a).
+//
+// Serves `Transpose<V,I,X,Y,J>` (reference src/view.rs:586-592, 1266-1294) — and any other pure
+// index permutation of a single Array — whenever the axis that is contiguous in the SOURCE
+// (call it A) is not the output's innermost axis (call it B).  Everything else is batch.
+//
+//   out[batch, a, b]  (b has out stride 1)   =   src[batch', b, a]  (a has src stride 1)
+//
+// One CTA moves one tile of 64 B-rows x 16 chunks (16 bytes each) of A: 64x64 4-byte elements or
+// 64x32 8-byte elements, 16 KB of shared memory, both global directions 128-bit and coalesced:
+//   load : each thread reads 16 B along A (a warp covers 2 source rows x 256 B) and writes them
+//          with ONE 16-byte shared store at row b, chunk (a_chunk ^ swz(b));
+//   store: each thread assembles 16 B along B from CH scalar shared loads (one per source row) and
+//          writes one 16-byte global store; a warp covers 4 output rows x 128 B.
+// Swizzle swz(b) = (b / CH) & 7 makes both shared phases bank-conflict-free: a quarter warp's
+// 16-byte stores hit 8 distinct chunks, and in the read phase the 32 lanes (8 b-groups x 4 a's)
+// hit 8 distinct chunks x 4 distinct words.
+// Bit-exact by construction (pure data movement).  HBM-bound: algorithmic bytes = 2 x elements.
+#include "kernels.cuh"
+
+namespace mdim {
+
+template <int ES, bool VEC>
+__global__ void __launch_bounds__(kTrThreads) k_transpose(const __grid_constant__ TransposePlan T, void* __restrict__ out_v) {
+    constexpr int CH = 16 / ES;   // elements per 16-byte chunk
+    constexpr int EW = ES / 4;    // 32-bit words per element
+    constexpr int TA = 16 * CH;   // tile extent along A (elements)
+    constexpr int TB = 64;        // tile extent along B (rows of the source)
+    constexpr int PA = TA / 32;   // read-phase passes along A
+    __shared__ __align__(16) uint32_t smem[TB * 64];
+
+    const char* __restrict__ src = (const char*)T.src;
+    char* __restrict__ out = (char*)out_v;
+    const int tid = threadIdx.x;
+    // load-phase coordinates
+    const int aq = tid & 15, br = tid >> 4;
+    // read-phase coordinates
+    const int lane = tid & 31, w = tid >> 5;
+    const int bq_lo = lane & 7, a_lo = lane >> 3;
+
+    for (uint64_t tile = blockIdx.x; tile < T.n_tiles; tile += gridDim.x) {
+        const uint64_t tb = tile % T.tiles_b;
+        uint64_t r = tile / T.tiles_b;
+        const uint64_t ta = r % T.tiles_a;
+        uint64_t batch = r / T.tiles_a;
+        int64_t src_base = T.src_offset, out_base = 0;
+#pragma unroll
+        for (int k = kMaxRank - 1; k >= 0; --k) {
+            if (k < T.n_batch) {
+                const uint64_t c = batch % T.batch_len[k];
+                batch /= T.batch_len[k];
+                src_base += (int64_t)c * T.batch_src_stride[k];
+                out_base += (int64_t)c * T.batch_out_stride[k];
+            }
+        }
+        const uint64_t a0 = ta * TA, b0 = tb * TB;
+
+        // ---- load: global (contiguous along A) -> swizzled shared --------------------------------
+        uint4 v[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int b_l = p * 16 + br;
+            const uint64_t b = b0 + b_l, a = a0 + (uint64_t)aq * CH;
+            const int64_t e = src_base + (int64_t)b * T.src_stride_b + (int64_t)a;
+            v[p] = make_uint4(0, 0, 0, 0);
+            if constexpr (VEC) {
+                if (b < T.len_b && a < T.len_a)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(v[p].x), "=r"(v[p].y), "=r"(v[p].z), "=r"(v[p].w) : "l"(src + e * ES));
+            } else {
+                uint32_t wds[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    if (b < T.len_b && a + i < T.len_a) {
+                        if constexpr (ES == 4) wds[i] = __ldg((const uint32_t*)(src + (e + i) * 4));
+                        else { const uint2 t = __ldg((const uint2*)(src + (e + i) * 8)); wds[2 * i] = t.x; wds[2 * i + 1] = t.y; }
+                    }
+                }
+                v[p] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int b_l = p * 16 + br;
+            const int chunk = aq ^ ((b_l / CH) & 7);
+            *reinterpret_cast<uint4*>(&smem[b_l * 64 + chunk * 4]) = v[p];
+        }
+        __syncthreads();
+
+        // ---- store: shared (gathered along B) -> global (contiguous along B) ---------------------
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int a_l = 4 * (w + 8 * (p % PA)) + a_lo;
+            const int bq = bq_lo + 8 * (p / PA);
+            uint32_t wds[4];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int b_l = bq * CH + i;
+                const int word = b_l * 64 + (((a_l / CH) ^ (bq & 7)) * 4) + (a_l % CH) * EW;
+                if constexpr (ES == 4) wds[i] = smem[word];
+                else { const uint2 t = *reinterpret_cast<const uint2*>(&smem[word]); wds[2 * i] = t.x; wds[2 * i + 1] = t.y; }
+            }
+            const uint64_t a = a0 + a_l, b = b0 + (uint64_t)bq * CH;
+            const int64_t e = out_base + (int64_t)a * T.out_stride_a + (int64_t)b;
+            if constexpr (VEC) {
+                if (a < T.len_a && b < T.len_b)
+                    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(out + e * ES), "r"(wds[0]), "r"(wds[1]), "r"(wds[2]), "r"(wds[3]) : "memory");
+            } else {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    if (a < T.len_a && b + i < T.len_b) {
+                        if constexpr (ES == 4) *(uint32_t*)(out + (e + i) * 4) = wds[i];
+                        else *(uint2*)(out + (e + i) * 8) = make_uint2(wds[2 * i], wds[2 * i + 1]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t stream) {
+    const int ch = 16 / T.esize;
+    bool vec = ((uintptr_t)T.src + (uintptr_t)(T.src_offset * T.esize)) % 16 == 0 && ((uintptr_t)out % 16) == 0 && T.src_stride_b % ch == 0 &&
+               T.out_stride_a % ch == 0 && T.len_a % ch == 0 && T.len_b % ch == 0;
+    for (int k = 0; k < T.n_batch; ++k) vec = vec && T.batch_src_stride[k] % ch == 0 && T.batch_out_stride[k] % ch == 0;
+    if (T.esize == 4) {
+        if (vec) k_transpose<4, true><<<grid, kTrThreads, 0, stream>>>(T, out);
+        else k_transpose<4, false><<<grid, kTrThreads, 0, stream>>>(T, out);
+    } else {
+        if (vec) k_transpose<8, true><<<grid, kTrThreads, 0, stream>>>(T, out);
+        else k_transpose<8, false><<<grid, kTrThreads, 0, stream>>>(T, out);
+    }
+}
+
+int transpose_max_ctas_per_sm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_transpose<4, true>, kTrThreads, 0);
+    return n > 0 ? n : 1;
+}
+
+}  // namespace mdim

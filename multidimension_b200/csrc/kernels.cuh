@@ -1,0 +1,53 @@
+// kernels.cuh — __global__ entry points (sm_100a) and their host-side launch table.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "exec.cuh"
+#include "program.hpp"
+
+namespace mdim {
+
+constexpr int kEvalThreads = 256;
+
+// ------------------------------------------------------------------------------------------------
+// K1 / K3 / K5: the rank-N fused evaluator.  One thread = one output vector per loop trip; the
+// grid is either one trip per thread or a persistent multiple of the SM count (tunable).
+// All operands are read-only and never alias `out` (C-ABI contract), so loads use the
+// non-coherent path; stores are streaming (evict-first) because nothing re-reads the output.
+// ------------------------------------------------------------------------------------------------
+template <class Sig, class S, int V, int MAXD, bool WIDE, bool R1>
+__global__ void __launch_bounds__(kEvalThreads)
+k_eval(const __grid_constant__ Program P, void* __restrict__ out, ErrWord* __restrict__ err, uint64_t g_begin, uint64_t g_end) {
+    const uint64_t step = (uint64_t)gridDim.x * kEvalThreads;
+    for (uint64_t g = g_begin + (uint64_t)blockIdx.x * kEvalThreads + threadIdx.x; g < g_end; g += step)
+        eval_vector<Sig, S, V, MAXD, WIDE, R1>(P, out, err, g);
+}
+
+using EvalKernel = void (*)(const Program, void*, ErrWord*, uint64_t, uint64_t);
+
+struct EvalVariant {
+    const char* name;
+    int slot_bytes, vec, max_depth, wide, r1;
+    const SigInstr* sig;  // nullptr = interpreter
+    int sig_n;
+    EvalKernel fn;
+};
+
+// defined in k_eval_s32.cu / k_eval_s64.cu
+const EvalVariant* eval_variants_s32(int* n);
+const EvalVariant* eval_variants_s64(int* n);
+
+// ------------------------------------------------------------------------------------------------
+// K2: tiled transpose of one leaf (see k_transpose.cu)
+// ------------------------------------------------------------------------------------------------
+constexpr int kTrThreads = 256;
+void launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t stream);
+int transpose_max_ctas_per_sm();
+
+// ------------------------------------------------------------------------------------------------
+// K4: sequential-order last-axis fold, optionally fused with a broadcast epilogue (k_fold.cu)
+// ------------------------------------------------------------------------------------------------
+constexpr int kFoldThreads = 128;
+void launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream_t stream);
+
+}  // namespace mdim

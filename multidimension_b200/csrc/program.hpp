@@ -1,0 +1,166 @@
+// program.hpp — the flattened device program a View chain is lowered to.
+//
+// The host planner (plan.cpp) turns the C-ABI descriptor (include/mdim.h: mdim_expr, a post-order
+// node array in position space) into this POD, which is passed BY VALUE as a __grid_constant__
+// kernel parameter (constant bank; ~3.3 KB).  The kernels (kernels.cuh) execute it either through
+// the depth-specialised interpreter or through a compile-time signature (static op tree).
+//
+// Reference semantics each instruction carries are cited in exec.cuh next to its implementation.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/mdim.h"
+
+namespace mdim {
+
+constexpr int kMaxRank = MDIM_MAX_RANK;
+constexpr int kMaxInstr = 56;
+constexpr int kMaxAddr = 12;
+constexpr int kMaxPred = 16;
+constexpr int kMaxComp = 4;
+constexpr int kMaxDepth = 8;  // deepest value stack any instantiation supports
+
+enum Opc : uint8_t {
+    OPC_LEAF_VEC = 0,   // contiguous along the vector axis, aligned: 128-bit loads
+    OPC_LEAF_BCAST,     // stride 0 along the vector axis: one scalar load, replicated
+    OPC_LEAF_STRIDED,   // anything else: V scalar loads
+    OPC_IOTA,           // linear combination of coordinates
+    OPC_CONST,
+    OPC_UNARY,
+    OPC_BINARY,
+    OPC_MASK,           // set the lane-active mask from pred[slot .. slot+n)  (n = 0: all active)
+    OPC_SELECT,         // Diagonal: keep TOS where pred[slot .. slot+n) holds, else imm
+    OPC_GATHER,         // pops aux index components, bounds-checks, loads
+    OPC_FOLD_BEGIN,     // push acc = imm, reset reduction coordinates
+    OPC_FOLD_STEP,      // acc = acc (op) TOS; advance reduction coords; loop to pc = slot
+    OPC_COUNT
+};
+
+struct Instr {  // 16 bytes
+    uint8_t opc;
+    uint8_t dtype;  // result dtype (mdim_dtype)
+    uint8_t op;     // mdim_binary_op / mdim_unary_op
+    uint8_t aux;    // UNARY: source dtype; BINARY/FOLD_STEP: rhs dtype; GATHER: n_comp
+    uint16_t slot;  // LEAF/IOTA/GATHER: addr index; MASK/SELECT: first pred; FOLD_STEP: loop pc
+    uint16_t n;     // MASK/SELECT: pred count; BINARY/GATHER/FOLD_STEP: source node (error reports)
+    uint64_t imm;   // CONST value bits; SELECT zero; FOLD_BEGIN init
+};
+
+struct Addr {
+    const void* ptr;
+    int64_t offset;             // elements
+    int64_t stride[kMaxRank];   // elements per unit of each (coalesced) iteration axis
+    int64_t gstride[kMaxComp];  // GATHER: elements per unit of index component
+    uint64_t bound[kMaxComp];   // GATHER: size of index component
+    int32_t n_peers;            // GATHER over peer-mapped shards (see mdim_node.n_peers)
+    int32_t pad;
+};
+
+struct Pred {  // coord[a] == (b >= 0 ? coord[b] : c)
+    int32_t a, b;
+    uint64_t c;
+};
+
+struct PeerTab {
+    const void* peer[MDIM_MAX_PEERS];
+    uint64_t block;
+};
+
+enum ProgFlags : uint32_t {
+    PF_EXPLAIN = 1u,  // single-lane rerun that records mdim_error_info details
+};
+
+struct Program {
+    int32_t rank;      // coalesced output axes
+    int32_t red_rank;  // coalesced reduction axes
+    int32_t n_instr, n_addr, n_pred;
+    int32_t out_dtype;
+    int32_t vec;  // lanes per thread along the innermost output axis
+    uint32_t flags;
+    uint64_t length[kMaxRank];  // coalesced lengths: out axes then reduction axes (elements)
+    uint32_t div_mul[kMaxRank]; // magic multiplier/shift for the decode of out axis a, where the
+    uint32_t div_shr[kMaxRank]; // innermost out axis is counted in vectors (length/vec)
+    uint64_t n_vec;             // total output vectors = prod(out lengths) / vec
+    uint64_t red_count;         // prod(reduction lengths)
+    uint64_t explain_pos;       // PF_EXPLAIN: output position whose failure details to record
+    Instr instr[kMaxInstr];
+    Addr addr[kMaxAddr];
+    Pred pred[kMaxPred];
+    PeerTab peers;
+};
+
+// Device-side error word: kernels atomicMin the linear output position of a failing element;
+// the host then reruns that one element with PF_EXPLAIN to fill the details.
+struct ErrWord {
+    unsigned long long pos;  // ~0ull = no error
+    int32_t status, node, component, pad;
+    unsigned long long value, bound;
+};
+
+// ---- planning result ------------------------------------------------------------------------
+enum KernelKind : int32_t {
+    KK_EMPTY = 0,      // zero-length output: nothing to launch
+    KK_GENERIC = 1,    // rank-N evaluator (k_eval)
+    KK_STREAM = 2,     // rank-<=1 contiguous: k_eval with the decode compiled out
+    KK_TRANSPOSE = 3,  // tiled smem transpose of one leaf (k_transpose)
+    KK_FOLD_ROWS = 4,  // last-axis sequential fold (+ fused broadcast epilogue) (k_fold_rows)
+};
+
+struct TransposePlan {
+    const void* src;
+    int32_t esize;
+    int64_t src_offset;
+    // out index space: batch axes (coalesced) x [A] x mid axes x [B] where B is the out-inner axis
+    // (out stride 1) and A is the axis whose SOURCE stride is 1.
+    int32_t n_batch;             // number of remaining axes (all but A and B)
+    uint64_t batch_len[kMaxRank];
+    int64_t batch_src_stride[kMaxRank];
+    int64_t batch_out_stride[kMaxRank];
+    uint64_t len_a, len_b;       // extents of A and B
+    int64_t src_stride_b;        // source stride along B (A has source stride 1)
+    int64_t out_stride_a;        // out stride along A (B has out stride 1)
+    uint64_t tiles_a, tiles_b, n_tiles;
+};
+
+struct FoldRowsPlan {
+    const void* src;
+    int64_t src_offset;
+    uint64_t n_rows;   // number of independent rows
+    uint32_t row_len;  // reduction length (contiguous)
+    int32_t op;        // mdim_binary_op
+    int32_t dtype;
+    uint64_t init;
+    // epilogue: 0 = emit the fold (one value per row); 1 = out[r][k] = src[r][k] (eop) g(fold[r])
+    int32_t epilogue;
+    int32_t eop;          // binary op of the epilogue, src on the left
+    int32_t post_op;      // optional binary op applied to the fold before the epilogue (e.g. DIV)
+    int32_t has_post;
+    uint64_t post_imm;    // ... with this constant on the right
+    int32_t rows_per_cta;
+};
+
+struct Plan {
+    int32_t kind;
+    int32_t slot_bytes;  // 4 or 8: width of the value-stack slots
+    int32_t vec;
+    int32_t wide;        // 64-bit coordinates/strides
+    int32_t max_depth;
+    int32_t static_id;   // index into the signature registry, -1 = interpreted
+    uint64_t out_elems;
+    int32_t out_esize;
+    Program prog;
+    TransposePlan tr;
+    FoldRowsPlan fr;
+    char sig[kMaxInstr * 4 + 4];  // signature bytes (opc,dtype,op,aux per instruction)
+    int32_t sig_len;
+    char describe[192];
+};
+
+int plan_expr(const mdim_expr* e, uint32_t flags, Plan* plan, char* why, size_t why_len);
+int dtype_size(int dt);
+const char* status_string(int st);
+
+// Signature registry (defined with the kernels; the planner only needs lookup by bytes).
+int find_static_signature(const char* sig, int sig_len, int slot_bytes, int vec);
+
+}  // namespace mdim

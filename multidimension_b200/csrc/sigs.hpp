@@ -1,0 +1,53 @@
+// sigs.hpp — compile-time op-tree signatures with a pre-instantiated fused kernel.
+//
+// A signature is the (opcode, dtype, op, aux) sequence of the postfix device program; run-time
+// data (pointers, strides, immediates, predicates) still come from the Program parameter.  This is
+// the device-side counterpart of the reference monomorphising `Zip<Zip<A,B,Mul>,Scalar,Add>` etc.
+// into one specialised collect loop.  Anything not listed runs through the interpreter.
+#pragma once
+#include "exec.cuh"
+
+namespace mdim {
+
+#define MDIM_SIG(NAME, ...)                                                   \
+    struct NAME {                                                             \
+        static constexpr SigInstr code[] = {__VA_ARGS__};                     \
+        static constexpr int n = (int)(sizeof(code) / sizeof(SigInstr));      \
+    };
+
+#define I_LV(dt) {OPC_LEAF_VEC, dt, 0, 0}
+#define I_LB(dt) {OPC_LEAF_BCAST, dt, 0, 0}
+#define I_LS(dt) {OPC_LEAF_STRIDED, dt, 0, 0}
+#define I_CONST(dt) {OPC_CONST, dt, 0, 0}
+#define I_BIN(dt, op) {OPC_BINARY, dt, op, dt}
+#define I_SELECT(dt) {OPC_SELECT, dt, 0, 0}
+#define I_GATHER1(dt) {OPC_GATHER, dt, 0, 1}
+#define I_IOTA(dt) {OPC_IOTA, dt, 0, 0}
+
+// ---- 32-bit slot programs (f32) ----------------------------------------------------------------
+MDIM_SIG(SigCopyF32, I_LV(MDIM_F32))
+MDIM_SIG(SigAddF32, I_LV(MDIM_F32), I_LV(MDIM_F32), I_BIN(MDIM_F32, MDIM_ADD))
+MDIM_SIG(SigSubF32, I_LV(MDIM_F32), I_LV(MDIM_F32), I_BIN(MDIM_F32, MDIM_SUB))
+MDIM_SIG(SigMulF32, I_LV(MDIM_F32), I_LV(MDIM_F32), I_BIN(MDIM_F32, MDIM_MUL))
+MDIM_SIG(SigDivF32, I_LV(MDIM_F32), I_LV(MDIM_F32), I_BIN(MDIM_F32, MDIM_DIV))
+MDIM_SIG(SigAddCF32, I_LV(MDIM_F32), I_CONST(MDIM_F32), I_BIN(MDIM_F32, MDIM_ADD))
+MDIM_SIG(SigSubCF32, I_LV(MDIM_F32), I_CONST(MDIM_F32), I_BIN(MDIM_F32, MDIM_SUB))
+MDIM_SIG(SigMulCF32, I_LV(MDIM_F32), I_CONST(MDIM_F32), I_BIN(MDIM_F32, MDIM_MUL))
+MDIM_SIG(SigDivCF32, I_LV(MDIM_F32), I_CONST(MDIM_F32), I_BIN(MDIM_F32, MDIM_DIV))
+// BASELINE config 2: a.zip(b).map(|(x,y)| x*y+1)  ==  a*b + Scalar(1.0)
+MDIM_SIG(SigMulAddCF32, I_LV(MDIM_F32), I_LV(MDIM_F32), I_BIN(MDIM_F32, MDIM_MUL), I_CONST(MDIM_F32), I_BIN(MDIM_F32, MDIM_ADD))
+// BASELINE config 4b: a - mean.iso::<(usize,usize,())>()  and  a - (sums / Scalar(256.0)).iso()
+MDIM_SIG(SigSubBcastF32, I_LV(MDIM_F32), I_LB(MDIM_F32), I_BIN(MDIM_F32, MDIM_SUB))
+MDIM_SIG(SigSubBcastDivF32, I_LV(MDIM_F32), I_LB(MDIM_F32), I_CONST(MDIM_F32), I_BIN(MDIM_F32, MDIM_DIV), I_BIN(MDIM_F32, MDIM_SUB))
+// BASELINE config 5: transpose -> diagonal(0.0) -> zip(w broadcast) -> x*y+1
+MDIM_SIG(SigDiagMulAddCF32, I_LB(MDIM_F32), I_SELECT(MDIM_F32), I_LV(MDIM_F32), I_BIN(MDIM_F32, MDIM_MUL), I_CONST(MDIM_F32),
+         I_BIN(MDIM_F32, MDIM_ADD))
+
+// ---- 64-bit slot programs ----------------------------------------------------------------------
+MDIM_SIG(SigCopyU64, I_LV(MDIM_U64))
+MDIM_SIG(SigIotaU64, I_IOTA(MDIM_U64))
+// BASELINE config 3: idx.compose(src): Array<usize,usize> selecting from Array<usize,f32>
+MDIM_SIG(SigGatherF32, I_LV(MDIM_U64), I_GATHER1(MDIM_F32))
+MDIM_SIG(SigGatherU64, I_LV(MDIM_U64), I_GATHER1(MDIM_U64))
+
+}  // namespace mdim
