@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py — effective HBM GB/s of View -> collect() (BASELINE.json metric).
+
+A step is ONE collect() of BASELINE config 2 — `a.zip(b).map(|(x,y)| x*y+1)` over two 2^30-element
+f32 Arrays per GPU (12 GiB of algorithmic traffic per step per GPU) — through the C ABI.  With N>1
+(torchrun, one process per GPU) the global Array is partitioned along its outermost index: every
+rank collects its own 2^30-element block, no data-path collective, weak scaling.
+
+  value     device-resident: K back-to-back collects, CUDA events on the launching stream, max over ranks
+  e2e       the same collect through mdim_collect_host: operands and result in pinned HOST memory,
+            H2D/D2H copies inside the timed region (chunked and overlapped by the library)
+  roofline  the fused elementwise kernel against the measured HBM copy rate (MEASURED_PEAKS.json)
+  ops       the other BASELINE configs (transpose, gather, fold+broadcast-subtract, rank-5 chain), N=1
+  cpu_baseline   the CPU oracle (a restatement of the reference's single-threaded collect(); the Rust
+            crate itself cannot be built here) on a bounded sample of the same workload
+
+`--impl reference` times that CPU restatement alone, as the reference arm.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+METRIC = "effective HBM GB/s for View->collect (zip+map x*y+1 over two 2^30-element f32 Arrays per GPU)"
+UNIT = "GB/s"
+N_ELEMS = 1 << 30
+WORKLOAD = "configs[1]: zip+map elementwise collect of two 2^30-element f32 Arrays (a.zip(b).map(|(x,y)| x*y+1))"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def known_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, device):
+        self.samples, self.reasons, self.stop_flag, self.max_mhz, self.thread = [], set(), False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv:
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join()
+            self.thread = None
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---- the CPU restatement (reference arm and cpu_baseline) -----------------------------------------------
+def cpu_oracle_pass(n, repeat, seed=1):
+    """Time `repeat` single-threaded oracle collects of config 2 over an n-element sample.
+    Returns (seconds per pass, algorithmic bytes per pass)."""
+    from helpers import oracle_lib
+    import multidimension_b200 as P
+    from multidimension_b200 import lowering as L
+    from multidimension_b200.view import _flat
+    rng = np.random.default_rng(seed)
+    a = P.Array.new(P.usize, n, rng.uniform(-1, 1, n).astype(np.float32))
+    b = P.Array.new(P.usize, n, rng.uniform(-1, 1, n).astype(np.float32))
+    view = a.zip(b).map(lambda p: p[0] * p[1] + np.float32(1))
+    groups, value = view._lower()
+    em = L.emit(value, _flat(groups), "host")
+    out = np.empty(n, dtype=np.float32)
+    lib = oracle_lib()
+    times = []
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        st = lib.mdim_oracle_collect(C.byref(em.expr), out.ctypes.data, None)
+        times.append(time.perf_counter() - t0)
+        assert st == 0
+    want = a.as_ref() * b.as_ref() + np.float32(1)
+    assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
+    return times, 12 * n
+
+
+def pin_to_one_core():
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        os.sched_setaffinity(0, {cores[-1]})
+    except Exception:
+        pass
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    pin_to_one_core()
+    n = 1 << 24  # bounded sample: 2^24 of the 2^30 elements per step
+    times, nbytes = cpu_oracle_pass(n, args.warmup + args.steps)
+    timed = times[args.warmup:]
+    sec = sum(timed) / len(timed)
+    v = nbytes / sec / 1e9
+    sample = f"{n} of {N_ELEMS} elements per step (same expression, same generator), single thread pinned to one core"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample,
+                   "note": "CPU restatement of the reference's single-threaded collect() (oracle/mdim_oracle.c); the Rust crate cannot be built in this image"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---- the B200 arm ------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2-elems", type=int, default=30, help="elements per GPU (default 2^30 = the BASELINE config)")
+    ap.add_argument("--no-ops", action="store_true", help="skip the per-op table (configs 1, 3, 4, 5)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import multidimension_b200 as P
+    from multidimension_b200 import usize, Array, Scalar, _ffi as F
+    from multidimension_b200.runtime import Storage
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = P.Context(local)
+    P.set_default_context(ctx)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    n = 1 << args.log2_elems
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_array(I, size, t, T):
+        return Array.from_device(I, size, t.data_ptr(), T, ctx=ctx, keep=t)
+
+    def out_storage(t, dtype):
+        return Storage.wrap_device(ctx, dtype, t.numel(), t.data_ptr(), keep=t)
+
+    def time_launches(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ctx.sync()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, ctx.launch_count() - l0
+
+    # ---- config 2, device-resident ---------------------------------------------------------------------
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0x5EED0001 + rank)
+    ta = torch.empty(n, device="cuda", dtype=torch.float32).uniform_(-1, 1, generator=g)
+    tb = torch.empty(n, device="cuda", dtype=torch.float32).uniform_(-1, 1, generator=g)
+    tout = torch.empty(n, device="cuda", dtype=torch.float32)
+    a, b = dev_array(usize, n, ta, "f32"), dev_array(usize, n, tb, "f32")
+    view = a.zip(b).map(lambda p: p[0] * p[1] + np.float32(1))
+    plan_text = view.describe()
+    st_out = out_storage(tout, F.F32)
+    # parity gate before any number: bit-exact against separately rounded mul and add
+    view.collect(out=st_out)
+    want = ta * tb
+    want += 1.0
+    assert torch.equal(tout.view(torch.int32), want.view(torch.int32)), "config 2 result is not bit-exact"
+    del want
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms_step, launches = time_launches(lambda: view.collect(out=st_out, flags=F.COLLECT_ASYNC), args.steps, args.warmup)
+    clocks.stop()
+    alg_bytes = 12 * n
+    per_gpu = alg_bytes / (ms_step * 1e-3) / 1e9
+    value = per_gpu * world
+    peak, peak_src = measured_peak()
+
+    result = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "elements_per_gpu": n, "algorithmic_bytes_per_step_per_gpu": alg_bytes,
+                   "parallelism": f"outermost-index shards x{world}, no collective", "kernel": plan_text,
+                   "l2": "operands (8 GiB) and result (4 GiB) are far larger than the 126 MB L2; no flush needed",
+                   "parity": "bit-exact vs separately rounded f32 mul/add, checked in this run"},
+        "clocks": clocks.summary(),
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
+                     "frac_of_nominal_8000": per_gpu / 8000.0, "peak_source": peak_src,
+                     "kernel": "k_eval<SigMulAddCF32, u32, V=8, R1>", "traffic": known_traffic("k_eval_SigMulAddCF32")},
+    }
+
+    # ---- e2e: host buffers through mdim_collect_host ---------------------------------------------------------------------
+    if not args.no_e2e:
+        ha, hb, ho = (Storage.pinned(ctx, F.F32, n) for _ in range(3))
+        ctx.download(ha.host, ta.data_ptr())
+        ctx.download(hb.host, tb.data_ptr())
+        hview = Array(usize, n, ha, "f32").zip(Array(usize, n, hb, "f32")).map(lambda p: p[0] * p[1] + np.float32(1))
+        e2e_steps = args.e2e_steps or max(1, min(args.steps, 5))
+        hview.collect(out=ho)  # warm-up: grows the staging arena
+        barrier()
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            hview.collect(out=ho)
+        barrier()
+        sec = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        chk = torch.from_numpy(ho.host[: 1 << 22]).cuda()
+        assert torch.equal(chk.view(torch.int32), tout[: 1 << 22].view(torch.int32)), "e2e result differs from the device-resident result"
+        result["e2e"] = {"value": alg_bytes * world / sec / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4 * n,
+                         "ms_per_step": sec * 1e3, "steps": e2e_steps, "kernels_per_step": (ctx.launch_count() - l0) // e2e_steps,
+                         "pcie_gbs": 12 * n / sec / 1e9}
+        del ha, hb, ho, hview
+
+    # ---- the other BASELINE configs, one line each (N=1 only) ------------------------------------------------------------------
+    if not args.no_ops and world == 1:
+        result["ops"] = bench_ops(ctx, torch, ta, tout, dev_array, out_storage, time_launches, peak, args)
+
+    # ---- CPU restatement beside it (rank 0, N=1) -----------------------------------------------------------------------------------
+    if not args.no_cpu and world == 1 and rank == 0:
+        pin_to_one_core()
+        sample_n = 1 << 26
+        times, nbytes = cpu_oracle_pass(sample_n, 2)
+        result["cpu_baseline"] = {"value": nbytes / min(times) / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+                                  "sample": f"{sample_n} of {N_ELEMS} elements of config 2, 2 passes (best), single thread; "
+                                            f"oracle/mdim_oracle.c restates the reference's collect() (no Rust toolchain in this image)",
+                                  "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_ops(ctx, torch, ta, tout, dev_array, out_storage, time_launches, peak, args):
+    """Configs 1, 3, 4, 5 of BASELINE.json at full size: GB/s on algorithmic bytes, each parity-gated."""
+    import multidimension_b200 as P
+    from multidimension_b200 import usize, Array, Scalar, Add, fold_rows, _ffi as F
+    ops = {}
+    steps = max(5, min(args.steps, 20))
+
+    def line(name, alg_bytes, ms, plan, **extra):
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        ops[name] = dict({"GB/s": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 4), "frac_of_nominal_8000": round(gbs / 8000.0, 4),
+                          "ms": round(ms, 5), "algorithmic_bytes": alg_bytes, "kernel": plan}, **extra)
+
+    # C1: 4096x4096 f32 transpose; 16 rotating source/destination pairs (2 GiB) keep it out of L2
+    R = 16
+    n1 = 4096
+    srcs = ta[: R * n1 * n1].view(R, n1 * n1)
+    dsts = tout[: R * n1 * n1].view(R, n1 * n1)
+    views = [dev_array((usize, usize), (n1, n1), srcs[k], "f32").transpose((), usize, usize, ()) for k in range(R)]
+    outs = [out_storage(dsts[k], F.F32) for k in range(R)]
+    views[0].collect(out=outs[0])
+    assert torch.equal(dsts[0].view(n1, n1), srcs[0].view(n1, n1).t()), "transpose mismatch"
+    state = {"k": 0}
+
+    def tr():
+        k = state["k"] = (state["k"] + 1) % R
+        views[k].collect(out=outs[k], flags=F.COLLECT_ASYNC)
+    ms, _ = time_launches(tr, steps * R, R)
+    line("c1_transpose_4096x4096_f32", 2 * 4 * n1 * n1, ms, views[0].describe(), l2="16 rotating buffer pairs (2 GiB total)")
+
+    # C3: compose — 2^28 uniform random usize indices into the 2^30-element f32 Array
+    n3 = 1 << 28
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0x5EED0003)
+    tidx = torch.randint(0, ta.numel(), (n3,), device="cuda", dtype=torch.int64, generator=g)
+    idx = dev_array(usize, n3, tidx, usize)
+    src = dev_array(usize, ta.numel(), ta, "f32")
+    v3 = idx.compose(src)
+    o3 = out_storage(tout[:n3], F.F32)
+    v3.collect(out=o3)
+    assert torch.equal(tout[:n3], ta[tidx]), "gather mismatch"
+    ms, _ = time_launches(lambda: v3.collect(out=o3, flags=F.COLLECT_ASYNC), steps, 3)
+    line("c3_compose_gather_2^28_from_2^30", 8 * n3 + 4 * n3 + 4 * n3, ms, v3.describe(),
+         sector_bytes=8 * n3 + 4 * n3 + 32 * n3, sector_GBs=round((8 + 4 + 32) * n3 / (ms * 1e-3) / 1e9, 1))
+    del tidx, idx, v3
+
+    # C4: (1024,1024,256) f32: sum over the last index (sequential order) and subtract the mean
+    shape = (1024, 1024, 256)
+    n4 = shape[0] * shape[1] * shape[2]
+    t4 = ta[:n4]
+    t4.uniform_(0, 1)
+    a4 = dev_array((usize, usize, usize), shape, t4, "f32")
+    sums = fold_rows(a4, (usize, usize), usize, Add, np.float32(0))
+    tsum = torch.empty(shape[0] * shape[1], device="cuda", dtype=torch.float32)
+    osum = out_storage(tsum, F.F32)
+    sums.collect(out=osum)
+    ref64 = t4.view(-1, 256).double().sum(dim=1)
+    rel = ((tsum.double() - ref64).abs() / ref64.abs()).max().item()
+    assert rel < 1e-6, f"fold error {rel}"
+    ms, _ = time_launches(lambda: sums.collect(out=osum, flags=F.COLLECT_ASYNC), steps, 3)
+    line("c4a_fold_sum_last_axis", 4 * n4 + 4 * shape[0] * shape[1], ms, sums.describe(), max_rel_err_vs_f64=rel)
+    fused = a4 - (sums / Scalar(256.0, "f32")).iso((usize, usize, ()))
+    o4 = out_storage(tout[:n4], F.F32)
+    fused.collect(out=o4)
+    want = t4.view(-1, 256) - (tsum / 256.0).unsqueeze(1)
+    assert torch.equal(tout[:n4].view(-1, 256), want), "fused fold+subtract mismatch"
+    del want
+    ms, _ = time_launches(lambda: fused.collect(out=o4, flags=F.COLLECT_ASYNC), steps, 3)
+    line("c4c_fold_mean_subtract_fused", 8 * n4, ms, fused.describe())
+    means = dev_array((usize, usize), shape[:2], tsum, "f32")
+    sub = a4 - means.iso((usize, usize, ()))
+    ms, _ = time_launches(lambda: sub.collect(out=o4, flags=F.COLLECT_ASYNC), steps, 3)
+    line("c4b_broadcast_subtract", 8 * n4 + 4 * shape[0] * shape[1], ms, sub.describe())
+
+    # C5: rank-5 chain transpose -> diagonal -> broadcast -> map, P=Q=R=64: 2^30 outputs, write-bound
+    Pn = Qn = Rn = 64
+    ta5 = torch.empty(Pn * Qn, device="cuda", dtype=torch.float32).uniform_(-1, 1)
+    tw5 = torch.empty(Rn, device="cuda", dtype=torch.float32).uniform_(-1, 1)
+    a5 = dev_array((usize, usize), (Pn, Qn), ta5, "f32")
+    w5 = dev_array(usize, Rn, tw5, "f32")
+    v5 = (a5.transpose((), usize, usize, ()).diagonal(np.float32(0)).iso((((usize, usize), (usize, usize)), ()))
+          .zip(w5.iso(((), usize))).map(lambda p: p[0] * p[1] + np.float32(1)))
+    o5 = out_storage(tout, F.F32)
+    v5.collect(out=o5)
+    eye = torch.eye(Pn * Qn, device="cuda", dtype=torch.float32)
+    t_qp = ta5.view(Pn, Qn).t().reshape(-1)
+    d = (eye * t_qp.unsqueeze(0))  # [(q,p),(q',p')]
+    want5 = d.reshape(-1, 1) * tw5.view(1, Rn)
+    want5 += 1.0
+    assert torch.equal(tout.view(-1, Rn), want5), "rank-5 chain mismatch"
+    del want5, d, eye
+    ms, _ = time_launches(lambda: v5.collect(out=o5, flags=F.COLLECT_ASYNC), steps, 3)
+    line("c5_rank5_transpose_diagonal_broadcast_map", 4 * (1 << 30) + 4 * Pn * Qn + 4 * Rn, ms, v5.describe())
+    return ops
+
+
+if __name__ == "__main__":
+    main()

@@ -625,11 +625,12 @@ MDIM_FN void run_interp(const Program& P, ErrWord* err, S (&st)[MAXD][V], Thread
 
 // Fast unsigned division by a run-time constant for n < 2^31 (planner guarantees the range):
 // q = umulhi(n, mul) >> shr.
+// mul == 0 encodes division by 1.
 MDIM_FN uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t shr) {
 #if defined(__CUDA_ARCH__)
-    return __umulhi(n, mul) >> shr;
+    return mul ? __umulhi(n, mul) >> shr : n;
 #else
-    return (uint32_t)(((uint64_t)n * mul) >> 32) >> shr;
+    return mul ? (uint32_t)(((uint64_t)n * mul) >> 32) >> shr : n;
 #endif
 }
 

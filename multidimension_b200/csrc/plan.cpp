@@ -80,6 +80,7 @@ struct Builder {
     // per original node: canonical strides (LEAF/IOTA/GATHER)
     int64_t cstride[MDIM_MAX_NODES][kMaxRank];
     int depth = 0, max_depth = 0;
+    int force_vec = 0;  // 0 = widest that divides the innermost axis
 
     int validate();
     void canonical_axes();
@@ -407,6 +408,7 @@ int Builder::emit() {
         for (int i = 0; i < 3; ++i)
             if (len[rank - 1] % (uint64_t)cand[i] == 0) { V = cand[i]; break; }
     }
+    if (force_vec) V = force_vec;
     plan->vec = V; P.vec = V;
     P.n_vec = out_elems / (uint64_t)V;
 
@@ -495,7 +497,9 @@ int Builder::detect_fast_paths() {
             if (with_red && s[n_axes - 1] != 1) return false;
             return true;
         };
-        if (es == 4 && row_len >= 8 && row_len <= 1024 && row_len % 4 == 0 && F.op != MDIM_SHL && F.op != MDIM_SHR) {
+        // the row kernel has no error channel: integer DIV/REM (which can panic) stay on the evaluator
+        auto row_safe = [&](int op) { return op != MDIM_SHL && op != MDIM_SHR && !(is_int(F.dtype) && (op == MDIM_DIV || op == MDIM_REM)); };
+        if (es == 4 && row_len >= 8 && row_len <= 1024 && row_len % 4 == 0 && row_safe(F.op)) {
             FoldRowsPlan& R = plan->fr;
             memset(&R, 0, sizeof R);
             R.row_len = (uint32_t)row_len; R.op = F.op; R.dtype = F.dtype; R.init = F.imm.u64 & 0xffffffffull;
@@ -520,7 +524,7 @@ int Builder::detect_fast_paths() {
                 if (fnode >= 0 && N[lx].kind == MDIM_NODE_LEAF && N[lx].dtype == F.dtype && N[fc].kind == MDIM_NODE_LEAF && N[fc].dtype == F.dtype &&
                     N[lx].data == N[fc].data && N[lx].offset == N[fc].offset && cstride[lx][0] == (int64_t)row_len && cstride[lx][1] == 1 &&
                     cstride[lx][2] == 0 && cstride[fc][0] == (int64_t)row_len && cstride[fc][1] == 0 && cstride[fc][2] == 1 && src_aligned &&
-                    N[root].op != MDIM_SHL && N[root].op != MDIM_SHR && post_op != MDIM_SHL && post_op != MDIM_SHR) {
+                    row_safe(N[root].op) && row_safe(post_op)) {
                     R.src = N[lx].data; R.src_offset = N[lx].offset; R.n_rows = len[0]; R.epilogue = 1; R.eop = N[root].op;
                     R.has_post = has_post; R.post_op = post_op; R.post_imm = post_imm;
                     plan->kind = KK_FOLD_ROWS;
@@ -556,6 +560,11 @@ int plan_expr(const mdim_expr* e, uint32_t flags, Plan* plan, char* why_buf, siz
     b->canonical_axes();
     st = b->emit();
     if (st) { delete b; return st; }
+    if (plan->max_depth > 4 && plan->vec > 1) {  // deep value stacks only exist scalar (register budget)
+        b->force_vec = 1;
+        st = b->emit();
+        if (st) { delete b; return st; }
+    }
     plan->kind = (b->rank <= 1 && b->red_rank == 0) ? KK_STREAM : KK_GENERIC;
     if (!(flags & MDIM_COLLECT_NO_STATIC))
         plan->static_id = find_static_signature(plan->sig, plan->sig_len, plan->slot_bytes, plan->vec);

@@ -1,0 +1,256 @@
+"""Expression lowering: lazy View tree -> flattened position-space descriptor (mdim_expr).
+
+This is the half of the north star that lives in src/view.rs in a Rust build ("expression
+lowering and descriptor emission"): every reference node type is re-stated as a transformation of
+a small scalar expression tree whose addressed nodes carry strides against NAMED position axes.
+Index-remapping views (Transpose, Iso, Coat, Row, Column, FromUsize, ToUsize, InsertOne,
+RemoveOne, broadcast in Zip) never touch data: they reorder, rename, split or pin axes, i.e. they
+rewrite strides and offsets.  At `collect()` the root view's axes are numbered in to_usize order
+(row-major, index.rs:109-114), the tree is written out in post-order as mdim_node[], and the
+C ABI runs it as one fused kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import struct
+
+from . import _ffi as F
+
+
+class Unsupported(F.MdimError):
+    """Valid in the reference, but not lowerable to the device (MDIM_ERR_UNSUPPORTED)."""
+
+    def __init__(self, message):
+        super().__init__(F.ERR_UNSUPPORTED, message)
+
+
+class Axis:
+    """One position-space axis (a leaf of a flattened index type) with its run-time length."""
+    __slots__ = ("length", "tag")
+    _count = 0
+
+    def __init__(self, length):
+        self.length = int(length)
+        Axis._count += 1
+        self.tag = Axis._count
+
+    def __repr__(self):
+        return f"ax{self.tag}[{self.length}]"
+
+
+class Node:
+    """One scalar-valued node.  `stride` maps Axis -> elements per step (absent = 0 = broadcast)."""
+    __slots__ = ("kind", "dtype", "op", "children", "buf", "offset", "stride", "gstride", "bound", "pairs", "imm",
+                 "src_dtype", "red_axes", "peers", "peer_block")
+
+    def __init__(self, kind, dtype, **kw):
+        self.kind = kind
+        self.dtype = dtype
+        self.op = kw.get("op", 0)
+        self.children = kw.get("children", ())
+        self.buf = kw.get("buf")            # storage object exposing .ptr (keeps the Array alive)
+        self.offset = kw.get("offset", 0)
+        self.stride = kw.get("stride", {})  # {Axis: int}
+        self.gstride = kw.get("gstride", ())
+        self.bound = kw.get("bound", ())
+        self.pairs = kw.get("pairs", ())    # DIAG: ((Axis, Axis | int), ...)
+        self.imm = kw.get("imm", 0)         # raw python value of `dtype`
+        self.src_dtype = kw.get("src_dtype", 0)
+        self.red_axes = kw.get("red_axes", ())  # FOLD: reduction axes, iterated last-fastest
+        self.peers = kw.get("peers")
+        self.peer_block = kw.get("peer_block", 0)
+
+    def clone(self, **kw):
+        n = Node(self.kind, self.dtype, op=self.op, children=self.children, buf=self.buf, offset=self.offset,
+                 stride=self.stride, gstride=self.gstride, bound=self.bound, pairs=self.pairs, imm=self.imm,
+                 src_dtype=self.src_dtype, red_axes=self.red_axes, peers=self.peers, peer_block=self.peer_block)
+        for k, v in kw.items():
+            setattr(n, k, v)
+        return n
+
+
+# A VALUE is a Node (scalar element) or a tuple of values (tuple-typed element, e.g. the pairs of
+# `zip`, src/ops.rs:25-29, or the compound indices of `All<(I,J)>`, src/index.rs:177-186).
+def map_value(value, fn):
+    if isinstance(value, tuple):
+        return tuple(map_value(v, fn) for v in value)
+    return fn(value)
+
+
+def flatten_value(value):
+    if isinstance(value, tuple):
+        out = []
+        for v in value:
+            out.extend(flatten_value(v))
+        return out
+    return [value]
+
+
+class Sub:
+    """Substitution of one old axis: coordinate = const + sum(coef * new_axis)."""
+    __slots__ = ("const", "terms")
+
+    def __init__(self, const=0, terms=()):
+        self.const = const
+        self.terms = tuple(terms)  # ((Axis, coef), ...)
+
+
+def substitute(node, table, memo=None):
+    """Rewrite every reference to the axes in `table` ({Axis: Sub}).  Linear in strides/offsets:
+    stride'[n] += stride[a] * coef, offset' += stride[a] * const.  Shared subtrees stay shared."""
+    if not table:
+        return node
+    if memo is None:
+        memo = {}
+    key = id(node)
+    if key in memo:
+        return memo[key]
+    kids = tuple(substitute(c, table, memo) for c in node.children)
+    out = node
+    changed = any(k is not c for k, c in zip(kids, node.children))
+    if node.kind in (F.LEAF, F.IOTA, F.GATHER) and any(a in table for a in node.stride):
+        stride, offset = {}, node.offset
+        for a, s in node.stride.items():
+            sub = table.get(a)
+            if sub is None:
+                stride[a] = stride.get(a, 0) + s
+            else:
+                offset += s * sub.const
+                for n, coef in sub.terms:
+                    stride[n] = stride.get(n, 0) + s * coef
+        out = node.clone(stride={a: s for a, s in stride.items() if s != 0}, offset=offset, children=kids)
+    elif node.kind == F.DIAG and any((a in table) or (not isinstance(b, int) and b in table) for a, b in node.pairs):
+        pairs, dead = [], False
+        for a, b in node.pairs:
+            a2, b2 = _sub_pred_side(a, table), _sub_pred_side(b, table)
+            if isinstance(a2, int) and isinstance(b2, int):
+                if a2 != b2:
+                    dead = True  # statically off the diagonal
+                continue
+            if isinstance(a2, int):
+                a2, b2 = b2, a2
+            pairs.append((a2, b2))
+        if dead:
+            out = Node(F.CONST, node.dtype, imm=node.imm)
+        elif not pairs:
+            out = kids[0]
+        else:
+            out = node.clone(pairs=tuple(pairs), children=kids)
+    elif node.kind == F.FOLD and any(a in table for a in node.red_axes):
+        raise Unsupported("substitution of a reduction axis")
+    elif changed:
+        out = node.clone(children=kids)
+    memo[key] = out
+    return out
+
+
+def _sub_pred_side(x, table):
+    if isinstance(x, int):
+        return x
+    sub = table.get(x)
+    if sub is None:
+        return x
+    if not sub.terms:
+        return int(sub.const)
+    if len(sub.terms) == 1 and sub.terms[0][1] == 1 and sub.const == 0:
+        return sub.terms[0][0]
+    raise Unsupported("a Diagonal whose axis has been split or merged needs device div/mod")
+
+
+def rename(table):
+    return {a: Sub(0, ((b, 1),)) for a, b in table.items()}
+
+
+# ---- packing immediates -----------------------------------------------------------------------
+_PACK = {F.U8: "<B", F.I32: "<i", F.U32: "<I", F.I64: "<q", F.U64: "<Q", F.F32: "<f", F.F64: "<d"}
+
+
+def imm_bits(dtype, value):
+    if dtype in (F.F32, F.F64):
+        raw = struct.pack(_PACK[dtype], float(value))
+    else:
+        width = F.DTYPE_SIZE[dtype] * 8
+        v = int(value) & ((1 << width) - 1)
+        raw = v.to_bytes(F.DTYPE_SIZE[dtype], "little")
+    return int.from_bytes(raw.ljust(8, b"\0"), "little")
+
+
+# ---- emission -----------------------------------------------------------------------------------
+class Emitted:
+    """An mdim_expr plus everything that must stay alive while it is in use."""
+
+    def __init__(self, expr, nodes, keep, out_dtype, out_len, bufs):
+        self.expr, self.nodes, self.keep, self.out_dtype, self.out_len, self.bufs = expr, nodes, keep, out_dtype, out_len, bufs
+
+
+def emit(root, axes, location):
+    """root: scalar Node; axes: the output's position axes in to_usize order;
+    location: 'device' | 'host' — which pointer of each storage object to write."""
+    order = []   # post-order, children before parents; shared subtrees are emitted per use
+    red_axes = []
+
+    def visit(n):
+        for c in n.children:
+            visit(c)
+        if n.kind == F.FOLD:
+            if red_axes:
+                raise Unsupported("more than one fold in one expression")
+            red_axes.extend(n.red_axes)
+        order.append(n)
+    visit(root)
+    if len(order) > F.MAX_NODES:
+        raise Unsupported(f"expression has {len(order)} nodes (> {F.MAX_NODES})")
+    all_axes = list(axes) + red_axes
+    if len(all_axes) > F.MAX_RANK:
+        raise Unsupported(f"expression has {len(all_axes)} position axes (> {F.MAX_RANK})")
+    pos = {a: i for i, a in enumerate(all_axes)}
+    arr = (F.Node * len(order))()
+    bufs = []
+    for i, n in enumerate(order):
+        d = arr[i]
+        d.kind, d.dtype, d.op = n.kind, n.dtype, n.op
+        d.src_dtype = n.src_dtype
+        if n.kind in (F.LEAF, F.IOTA, F.GATHER):
+            d.offset = n.offset
+            for a, s in n.stride.items():
+                if a not in pos:
+                    raise Unsupported(f"internal: node strides over an axis that is not iterated ({a!r})")
+                d.stride[pos[a]] = s
+        if n.kind in (F.LEAF, F.GATHER):
+            if n.peers:
+                d.n_peers = len(n.peers)
+                for k, p in enumerate(n.peers):
+                    d.peer[k] = p
+                d.peer_block = n.peer_block
+            else:
+                d.data = n.buf.pointer(location)
+            bufs.append(n.buf)
+        if n.kind == F.GATHER:
+            d.n_comp = len(n.children)
+            for c in range(len(n.children)):
+                d.gstride[c] = n.gstride[c]
+                d.bound[c] = n.bound[c]
+        if n.kind == F.DIAG:
+            d.n_comp = len(n.pairs)
+            for p, (a, b) in enumerate(n.pairs):
+                d.axis_a[p] = pos[a]
+                if isinstance(b, int):
+                    d.axis_b[p] = -1
+                    d.axis_c[p] = b
+                else:
+                    d.axis_b[p] = pos[b]
+            d.imm.u64 = imm_bits(n.dtype, n.imm)
+        if n.kind in (F.CONST, F.FOLD):
+            d.imm.u64 = imm_bits(n.dtype, n.imm)
+    e = F.Expr()
+    e.abi_version = F.ABI_VERSION
+    e.rank = len(axes)
+    e.red_rank = len(red_axes)
+    e.n_nodes = len(order)
+    for i, a in enumerate(all_axes):
+        e.length[i] = a.length
+    e.nodes = C.cast(arr, C.POINTER(F.Node))
+    out_len = 1
+    for a in axes:
+        out_len *= a.length
+    return Emitted(e, arr, order, root.dtype, out_len, bufs)

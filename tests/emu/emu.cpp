@@ -1,0 +1,77 @@
+// emu.cpp — TEST INFRASTRUCTURE (never linked into the product): compiles the product's host
+// planner (plan.cpp) and the product's per-thread evaluator (exec.cuh, host mode) with g++ and runs
+// the evaluator one "thread" at a time.  It lets the CPU-only test suite check descriptor ->
+// Program lowering, coordinate decode, vector/broadcast/strided loads, predicates, gather and fold
+// control flow, and error reporting against the oracle without a GPU.  The dedicated CUDA kernels
+// (tiled transpose, row fold) have no host form; the generic program stands in for them here.
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../multidimension_b200/csrc/exec.cuh"
+#include "../../multidimension_b200/csrc/plan.cpp"
+
+namespace mdim {
+int find_static_signature(const char*, int, int, int) { return -1; }
+
+template <class S, int V, int MAXD, bool WIDE>
+static void run_all(const Program& P, void* out, ErrWord* err, uint64_t g0, uint64_t g1) {
+    for (uint64_t g = g0; g < g1; ++g) eval_vector<NoSig, S, V, MAXD, WIDE, false>(P, out, err, g);
+}
+
+template <class S, int V, int MAXD>
+static void run_w(const Plan& p, const Program& P, void* out, ErrWord* err, uint64_t g0, uint64_t g1) {
+    if (p.wide) run_all<S, V, MAXD, true>(P, out, err, g0, g1);
+    else run_all<S, V, MAXD, false>(P, out, err, g0, g1);
+}
+
+static int run(const Plan& p, const Program& P, void* out, ErrWord* err, uint64_t g0, uint64_t g1) {
+    if (p.slot_bytes == 4) {
+        if (p.vec == 8 && p.max_depth <= 4) run_w<uint32_t, 8, 4>(p, P, out, err, g0, g1);
+        else if (p.vec == 4 && p.max_depth <= 4) run_w<uint32_t, 4, 4>(p, P, out, err, g0, g1);
+        else if (p.vec == 1 && p.max_depth <= 4) run_w<uint32_t, 1, 4>(p, P, out, err, g0, g1);
+        else if (p.vec == 1) run_w<uint32_t, 1, 8>(p, P, out, err, g0, g1);
+        else return MDIM_ERR_UNSUPPORTED;
+    } else {
+        if (p.vec == 4 && p.max_depth <= 4) run_w<uint64_t, 4, 4>(p, P, out, err, g0, g1);
+        else if (p.vec == 2 && p.max_depth <= 4) run_w<uint64_t, 2, 4>(p, P, out, err, g0, g1);
+        else if (p.vec == 1 && p.max_depth <= 4) run_w<uint64_t, 1, 4>(p, P, out, err, g0, g1);
+        else if (p.vec == 1) run_w<uint64_t, 1, 8>(p, P, out, err, g0, g1);
+        else return MDIM_ERR_UNSUPPORTED;
+    }
+    return MDIM_OK;
+}
+}  // namespace mdim
+
+extern "C" int mdim_emu_collect(const mdim_expr* e, void* out, uint32_t flags, mdim_error_info* info, char* describe, size_t describe_len) {
+    using namespace mdim;
+    Plan* plan = new Plan();
+    char why[160];
+    if (info) memset(info, 0, sizeof *info);
+    int st = plan_expr(e, flags, plan, why, sizeof why);
+    if (describe && describe_len) snprintf(describe, describe_len, "%s", st ? why : plan->describe);
+    if (st) { if (info) { info->status = st; snprintf(info->message, sizeof info->message, "%s", why); } delete plan; return st; }
+    if (plan->kind == KK_EMPTY) { delete plan; return MDIM_OK; }
+    ErrWord err;
+    memset(&err, 0, sizeof err);
+    err.pos = ~0ull;
+    st = run(*plan, plan->prog, out, &err, 0, plan->prog.n_vec);
+    if (st == MDIM_OK && err.pos != ~0ull) {
+        const uint64_t pos = err.pos;
+        Program q = plan->prog;
+        q.flags |= PF_EXPLAIN;
+        q.explain_pos = pos;
+        memset(&err, 0, sizeof err);
+        err.pos = ~0ull;
+        run(*plan, q, out, &err, pos / plan->vec, pos / plan->vec + 1);
+        st = err.status ? err.status : MDIM_ERR_INVALID;
+        if (info) {
+            info->status = st; info->node = err.node; info->position = pos; info->value = err.value; info->bound = err.bound;
+            info->component = err.component;
+            if (st == MDIM_ERR_OOB) snprintf(info->message, sizeof info->message, "Index %llu is out of bounds for size %llu",
+                                             (unsigned long long)err.value, (unsigned long long)err.bound);
+            else if (st == MDIM_ERR_ARITH) snprintf(info->message, sizeof info->message, "attempt to divide by zero or with overflow");
+        }
+    }
+    delete plan;
+    return st;
+}
