@@ -194,7 +194,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = P.Context(local)
     P.set_default_context(ctx)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # an explicit stream: handle 0 would select the context's own stream
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     n = 1 << args.log2_elems
 
@@ -293,6 +294,9 @@ def main():
                          "ms_per_step": sec * 1e3, "steps": e2e_steps, "kernels_per_step": (ctx.launch_count() - l0) // e2e_steps,
                          "pcie_gbs": 12 * n / sec / 1e9}
         del ha, hb, ho, hview
+        import gc
+        gc.collect()  # the 12 GiB of pinned memory must be released now, not inside a later timed region
+        torch.cuda.synchronize()
 
     # ---- the other BASELINE configs, one line each (N=1 only) ------------------------------------------------------------------
     if not args.no_ops and world == 1:
@@ -370,8 +374,10 @@ def bench_ops(ctx, torch, ta, tout, dev_array, out_storage, time_launches, peak,
     osum = out_storage(tsum, F.F32)
     sums.collect(out=osum)
     ref64 = t4.view(-1, 256).double().sum(dim=1)
-    rel = ((tsum.double() - ref64).abs() / ref64.abs()).max().item()
-    assert rel < 1e-6, f"fold error {rel}"
+    rel = ((tsum.double() - ref64).abs() / ref64.abs()).max().item()  # informational: error of the SEQUENTIAL f32 sum itself
+    rows = torch.arange(0, shape[0] * shape[1], 251, device="cuda")      # parity: bit-exact vs a sequential f32 sum on the host
+    seq = np.add.accumulate(t4.view(-1, 256)[rows].cpu().numpy(), axis=1, dtype=np.float32)[:, -1]
+    assert np.array_equal(seq.view(np.uint32), tsum[rows].cpu().numpy().view(np.uint32)), "fold is not in sequential order"
     ms, _ = time_launches(lambda: sums.collect(out=osum, flags=F.COLLECT_ASYNC), steps, 3)
     line("c4a_fold_sum_last_axis", 4 * n4 + 4 * shape[0] * shape[1], ms, sums.describe(), max_rel_err_vs_f64=rel)
     fused = a4 - (sums / Scalar(256.0, "f32")).iso((usize, usize, ()))

@@ -41,6 +41,7 @@ static bool sig_matches(const EvalVariant& v, const char* sig, int sig_len) {
         if (v.sig[i].opc != s[0] || v.sig[i].dtype != s[1]) return false;
         // op/aux only matter for the opcodes that read them
         const int opc = v.sig[i].opc;
+        if (opc == OPC_LEAF_VEC && v.sig[i].aux != s[3]) return false;
         if ((opc == OPC_BINARY || opc == OPC_UNARY || opc == OPC_FOLD_STEP) && (v.sig[i].op != s[2] || v.sig[i].aux != s[3])) return false;
         if (opc == OPC_GATHER && v.sig[i].aux != s[3]) return false;
     }
@@ -56,20 +57,18 @@ int find_static_signature(const char* sig, int sig_len, int slot_bytes, int vec)
 
 static const EvalVariant* select_variant(const Plan& p, bool force_interp) {
     const std::vector<EvalVariant>& R = registry();
-    const int want_r1 = p.kind == KK_STREAM ? 1 : 0;
+    const int need = p.kind == KK_STREAM ? 1 : std::max(1, p.n_axes);
+    const EvalVariant* best = nullptr;
     if (p.static_id >= 0 && !p.wide && !force_interp) {
-        const EvalVariant* best = nullptr;
         for (const EvalVariant& v : R) {
-            if (v.slot_bytes != p.slot_bytes || v.vec != p.vec || v.wide || !sig_matches(v, p.sig, p.sig_len)) continue;
-            if (v.r1 && !want_r1) continue;
-            if (!best || (v.r1 == want_r1 && best->r1 != want_r1)) best = &v;
+            if (v.slot_bytes != p.slot_bytes || v.vec != p.vec || v.wide || v.maxr < need || !sig_matches(v, p.sig, p.sig_len)) continue;
+            if (!best || v.maxr < best->maxr) best = &v;
         }
         if (best) return best;
     }
-    const EvalVariant* best = nullptr;
     for (const EvalVariant& v : R) {
-        if (v.sig || v.slot_bytes != p.slot_bytes || v.vec != p.vec || v.wide != p.wide || v.r1 || v.max_depth < p.max_depth) continue;
-        if (!best || v.max_depth < best->max_depth) best = &v;
+        if (v.sig || v.slot_bytes != p.slot_bytes || v.vec != p.vec || v.wide != p.wide || v.maxr < need || v.max_depth < p.max_depth) continue;
+        if (!best || v.maxr < best->maxr || (v.maxr == best->maxr && v.max_depth < best->max_depth)) best = &v;
     }
     return best;
 }
@@ -291,6 +290,9 @@ int mdim_init(int device, mdim_ctx** out) {
               cudaMalloc(&ctx->d_err, sizeof(ErrWord) * kErrSlots) == cudaSuccess &&
               cudaMallocHost(&ctx->h_err, sizeof(ErrWord) * kErrSlots) == cudaSuccess;
     if (ok) {
+        // Random gathers fetch whole L2 lines unless the fetch granularity is lowered (a per-device hint).
+        const int l2_fetch = env_int("MDIM_L2_FETCH", 0);
+        if (l2_fetch > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)l2_fetch);
         ctx->stream = ctx->own_stream;
         for (int i = 0; i < kErrSlots; ++i) { memset(&ctx->h_err[i], 0, sizeof(ErrWord)); ctx->h_err[i].pos = ~0ull; }
         ok = cudaMemcpy(ctx->d_err, ctx->h_err, sizeof(ErrWord) * kErrSlots, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -454,7 +456,7 @@ int mdim_plan_describe_nodevice(const mdim_expr* e, uint32_t flags, char* buf, s
     if (st) snprintf(buf, buf_len, "%s", why);
     else {
         const EvalVariant* v = (plan->kind == KK_GENERIC || plan->kind == KK_STREAM) ? select_variant(*plan, false) : nullptr;
-        if (v) snprintf(buf, buf_len, "%s [%s%s]", plan->describe, v->name, v->r1 ? " r1" : "");
+        if (v) snprintf(buf, buf_len, "%s [%s r%d]", plan->describe, v->name, v->maxr);
         else snprintf(buf, buf_len, "%s", plan->describe);
     }
     delete plan;

@@ -68,6 +68,9 @@ MDIM_FN int esize_of(int dt) { return dt == MDIM_U8 ? 1 : (dt == MDIM_I32 || dt 
 MDIM_FN void ld128_stream(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
 }
+MDIM_FN void ld128_cached(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+}
 MDIM_FN void ld64_stream(const void* p, uint32_t& a, uint32_t& b) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
 }
@@ -91,6 +94,7 @@ MDIM_FN void err_min(unsigned long long* p, unsigned long long v) { atomicMin(p,
 MDIM_FN void ld128_stream(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
     const uint32_t* q = (const uint32_t*)p; a = q[0]; b = q[1]; c = q[2]; d = q[3];
 }
+MDIM_FN void ld128_cached(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) { ld128_stream(p, a, b, c, d); }
 MDIM_FN void ld64_stream(const void* p, uint32_t& a, uint32_t& b) { const uint32_t* q = (const uint32_t*)p; a = q[0]; b = q[1]; }
 MDIM_FN uint32_t ld32_stream(const void* p) { return *(const uint32_t*)p; }
 MDIM_FN uint32_t ld32(const void* p) { return *(const uint32_t*)p; }
@@ -103,6 +107,10 @@ MDIM_FN void st8(void* p, uint32_t a) { *(uint8_t*)p = (uint8_t)a; }
 MDIM_FN void err_min(unsigned long long* p, unsigned long long v) { if (v < *p) *p = v; }
 #endif
 
+template <bool CACHED> MDIM_FN void ld128(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    if constexpr (CACHED) ld128_cached(p, a, b, c, d); else ld128_stream(p, a, b, c, d);
+}
+
 template <class S> MDIM_FN S ld_scalar(const void* base, int64_t idx, int esize) {
     if (esize == 4) return (S)ld32((const char*)base + idx * 4);
     if (esize == 1) return (S)ld8((const char*)base + idx);
@@ -111,14 +119,14 @@ template <class S> MDIM_FN S ld_scalar(const void* base, int64_t idx, int esize)
 }
 
 // V consecutive elements starting at element `idx`; the planner guarantees the alignment.
-template <class S, int V> MDIM_FN void ld_vector(const void* base, int64_t idx, int esize, S (&d)[V]) {
+template <class S, int V, bool CACHED> MDIM_FN void ld_vector(const void* base, int64_t idx, int esize, S (&d)[V]) {
     if (esize == 4) {
         const char* p = (const char*)base + idx * 4;
         if constexpr (V % 4 == 0) {
 #pragma unroll
             for (int i = 0; i < V; i += 4) {
                 uint32_t a, b, c, e;
-                ld128_stream(p + i * 4, a, b, c, e);
+                ld128<CACHED>(p + i * 4, a, b, c, e);
                 d[i] = a; d[i + 1] = b; d[i + 2] = c; d[i + 3] = e;
             }
         } else if constexpr (V == 2) {
@@ -133,7 +141,7 @@ template <class S, int V> MDIM_FN void ld_vector(const void* base, int64_t idx, 
 #pragma unroll
                 for (int i = 0; i < V; i += 2) {
                     uint32_t a, b, c, e;
-                    ld128_stream(p + i * 8, a, b, c, e);
+                    ld128<CACHED>(p + i * 8, a, b, c, e);
                     d[i] = (S)a | ((S)b << 32); d[i + 1] = (S)c | ((S)e << 32);
                 }
             } else {
@@ -366,51 +374,52 @@ template <class S> MDIM_FN S un_op(int op, int dt, int src_dt, S a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-thread state
+// per-thread state.  MAXR = number of iteration axes this instantiation walks (the planner picks the
+// smallest instantiation >= rank + red_rank; axes beyond the program's own have length 1, stride 0,
+// so no loop below ever tests the run-time rank).  MAXR == 1 is the contiguous stream form.
+// WIDE = 64-bit coordinates and offsets; otherwise the planner has proved that every coordinate,
+// every per-operand linear offset and every predicate value fits in 32 bits.
 // ------------------------------------------------------------------------------------------------
-template <bool WIDE> struct CoordTraits { using coord_t = uint32_t; using stride_t = int32_t; };
-template <> struct CoordTraits<true> { using coord_t = uint64_t; using stride_t = int64_t; };
+template <bool WIDE> struct CoordTraits { using coord_t = uint32_t; using off_t = int32_t; };
+template <> struct CoordTraits<true> { using coord_t = uint64_t; using off_t = int64_t; };
 
-template <bool WIDE> struct ThreadState {
-    typename CoordTraits<WIDE>::coord_t c[kMaxRank];  // element coordinates of lane 0
-    uint64_t pos0;                                    // linear output position of lane 0
-    uint64_t red_k;                                   // reduction step counter
-    uint32_t mask;                                    // lane-active mask (Diagonal laziness)
+template <bool WIDE, int MAXR> struct ThreadState {
+    typename CoordTraits<WIDE>::coord_t c[MAXR];  // element coordinates of lane 0
+    uint64_t pos0;                                // linear output position of lane 0
+    uint64_t red_k;                               // reduction step counter
+    uint32_t mask;                                // lane-active mask (Diagonal laziness)
 };
 
-template <bool WIDE> MDIM_FN int64_t addr_offset(const Program& P, int slot, const ThreadState<WIDE>& ts) {
-    using stride_t = typename CoordTraits<WIDE>::stride_t;
-    int64_t off = P.addr[slot].offset;
-    const int naxes = P.rank + P.red_rank;
+// offset + sum_a coord[a] * stride[a]: Index::to_usize of the operand's own index (src/index.rs:109-114)
+// after every Transpose/Iso/Row/Column/broadcast remapping has been folded into the strides.
+template <bool WIDE, int MAXR>
+MDIM_FN typename CoordTraits<WIDE>::off_t addr_offset(const Program& P, int slot, const ThreadState<WIDE, MAXR>& ts) {
+    using off_t = typename CoordTraits<WIDE>::off_t;
+    off_t off = (off_t)P.addr[slot].offset;
 #pragma unroll
-    for (int a = 0; a < kMaxRank; ++a)
-        if (a < naxes) off += (int64_t)(stride_t)ts.c[a] * (int64_t)(stride_t)P.addr[slot].stride[a];
+    for (int a = 0; a < MAXR; ++a) off += (off_t)ts.c[a] * (off_t)P.addr[slot].stride[a];
     return off;
 }
 
-template <bool WIDE> MDIM_FN int64_t inner_stride(const Program& P, int slot) {
-    return P.rank > 0 ? P.addr[slot].stride[P.rank - 1] : 0;
-}
+MDIM_FN int64_t inner_stride(const Program& P, int slot) { return P.addr[slot].inner; }
 
-// coordinate of `axis` for lane `lane` (only the innermost output axis varies across lanes)
-template <bool WIDE> MDIM_FN uint64_t lane_coord(const Program& P, const ThreadState<WIDE>& ts, int axis, int lane) {
-    // mask arithmetic rather than `if (a == axis) v = c[a]`: the compiler turns the latter back
-    // into a dynamically indexed load, which forces the coordinates into local memory
-    uint64_t v = 0;
-#pragma unroll
-    for (int a = 0; a < kMaxRank; ++a) v |= (uint64_t)ts.c[a] & (0ull - (uint64_t)(a == axis));
-    return axis == P.rank - 1 ? v + (uint64_t)lane : v;
-}
-
-template <int V, bool WIDE> MDIM_FN uint32_t eval_preds(const Program& P, const ThreadState<WIDE>& ts, int first, int n) {
+// Predicates are linear forms: sum_a coef[a] * coord[a] (+ lane * lane_coef) == rhs.
+// `coord[a] == coord[b]` is coef[a] = 1, coef[b] = -1, rhs = 0; `coord[a] == k` is coef[a] = 1, rhs = k.
+template <int V, bool WIDE, int MAXR>
+MDIM_FN uint32_t eval_preds(const Program& P, const ThreadState<WIDE, MAXR>& ts, int first, int n) {
+    using off_t = typename CoordTraits<WIDE>::off_t;
     uint32_t m = (1u << V) - 1u;
     for (int p = first; p < first + n; ++p) {
-        const int a = P.pred[p].a, b = P.pred[p].b;
+        off_t s = 0;
 #pragma unroll
-        for (int l = 0; l < V; ++l) {
-            const uint64_t lhs = lane_coord<WIDE>(P, ts, a, l);
-            const uint64_t rhs = b >= 0 ? lane_coord<WIDE>(P, ts, b, l) : P.pred[p].c;
-            if (lhs != rhs) m &= ~(1u << l);
+        for (int a = 0; a < MAXR; ++a) s += (off_t)ts.c[a] * (off_t)P.pred[p].coef[a];
+        const off_t rhs = (off_t)P.pred[p].rhs, lc = (off_t)P.pred[p].lane_coef;
+        if (lc == 0) {  // the vector axis is not involved: one test for all lanes
+            if (s != rhs) m = 0;
+        } else {
+#pragma unroll
+            for (int l = 0; l < V; ++l)
+                if (s + (off_t)l * lc != rhs) m &= ~(1u << l);
         }
     }
     return m;
@@ -438,12 +447,12 @@ MDIM_FN int depth_delta(int opc, int aux) {
 // Compose::at = w.at(v.at(i)) (src/view.rs:905,911); each component is bounds-checked like
 // usize::to_usize (src/int.rs:16-19) in component order; inactive (off-diagonal) lanes neither
 // load nor report, because Diagonal::at never evaluates its inner view there (src/view.rs:854-856).
-template <int D, int NC, class S, int V, int MAXD, bool WIDE>
-MDIM_FN void exec_gather(const Program& P, ErrWord* err, const Instr& I, S (&st)[MAXD][V], const ThreadState<WIDE>& ts) {
+template <int D, int NC, class S, int V, int MAXD, bool WIDE, int MAXR>
+MDIM_FN void exec_gather(const Program& P, ErrWord* err, const Instr& I, S (&st)[MAXD][V], const ThreadState<WIDE, MAXR>& ts) {
     if constexpr (sizeof(S) == 8 && D >= NC && NC >= 1) {
         const Addr& A = P.addr[I.slot];
-        const int64_t base = addr_offset<WIDE>(P, I.slot, ts);
-        const int64_t s_in = inner_stride<WIDE>(P, I.slot);
+        const int64_t base = (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts);
+        const int64_t s_in = inner_stride(P, I.slot);
         const int es = esize_of(I.dtype);
 #pragma unroll
         for (int l = 0; l < V; ++l) {
@@ -473,25 +482,29 @@ MDIM_FN void exec_gather(const Program& P, ErrWord* err, const Instr& I, S (&st)
 }
 
 // Execute instruction I at compile-time stack depth D.  Returns the next pc.
-template <int D, class S, int V, int MAXD, bool WIDE>
+template <int D, class S, int V, int MAXD, bool WIDE, int MAXR>
 MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int op, int aux, int pc,
-                       S (&st)[MAXD][V], ThreadState<WIDE>& ts) {
+                       S (&st)[MAXD][V], ThreadState<WIDE, MAXR>& ts) {
     const Instr& I = P.instr[pc];
     int next = pc + 1;
     switch (opc) {
         case OPC_LEAF_VEC:  // Array::at = items[to_usize(index)] (src/array.rs:81,86), V at a time
-            if constexpr (D < MAXD) ld_vector<S, V>(P.addr[I.slot].ptr, addr_offset<WIDE>(P, I.slot, ts), esize_of(dtype), st[D]);
+            if constexpr (D < MAXD) {
+                const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts);
+                if (aux) ld_vector<S, V, true>(P.addr[I.slot].ptr, off, esize_of(dtype), st[D]);   // re-read operand: keep in L1
+                else ld_vector<S, V, false>(P.addr[I.slot].ptr, off, esize_of(dtype), st[D]);      // read once: stream past L1
+            }
             break;
         case OPC_LEAF_BCAST:  // operand lacks the vector axis: Broadcast::index drops it (src/broadcast.rs:46-60)
             if constexpr (D < MAXD) {
-                const S v = ld_scalar<S>(P.addr[I.slot].ptr, addr_offset<WIDE>(P, I.slot, ts), esize_of(dtype));
+                const S v = ld_scalar<S>(P.addr[I.slot].ptr, (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts), esize_of(dtype));
 #pragma unroll
                 for (int l = 0; l < V; ++l) st[D][l] = v;
             }
             break;
         case OPC_LEAF_STRIDED:
             if constexpr (D < MAXD) {
-                const int64_t off = addr_offset<WIDE>(P, I.slot, ts), s_in = inner_stride<WIDE>(P, I.slot);
+                const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts), s_in = inner_stride(P, I.slot);
                 const int es = esize_of(dtype);
 #pragma unroll
                 for (int l = 0; l < V; ++l) st[D][l] = ld_scalar<S>(P.addr[I.slot].ptr, off + (int64_t)l * s_in, es);
@@ -499,7 +512,7 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
             break;
         case OPC_IOTA:  // All<I>::at(index) = index (src/index.rs:185)
             if constexpr (D < MAXD) {
-                const int64_t off = addr_offset<WIDE>(P, I.slot, ts), s_in = inner_stride<WIDE>(P, I.slot);
+                const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts), s_in = inner_stride(P, I.slot);
 #pragma unroll
                 for (int l = 0; l < V; ++l) {
                     const uint64_t x = (uint64_t)(off + (int64_t)l * s_in);
@@ -531,26 +544,26 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
             }
             break;
         case OPC_MASK:
-            ts.mask = I.n ? eval_preds<V, WIDE>(P, ts, I.slot, I.n) : ((1u << V) - 1u);
+            ts.mask = I.n ? eval_preds<V, WIDE, MAXR>(P, ts, I.slot, I.n) : ((1u << V) - 1u);
             break;
         case OPC_SELECT:  // Diagonal::at (src/view.rs:854-856)
             if constexpr (D >= 1) {
-                const uint32_t m = eval_preds<V, WIDE>(P, ts, I.slot, I.n);
+                const uint32_t m = eval_preds<V, WIDE, MAXR>(P, ts, I.slot, I.n);
 #pragma unroll
                 for (int l = 0; l < V; ++l) st[D - 1][l] = ((m >> l) & 1u) ? st[D - 1][l] : (S)I.imm;
             }
             break;
         case OPC_GATHER:
-            if (aux == 1) exec_gather<D, 1, S, V, MAXD, WIDE>(P, err, I, st, ts);
-            else if (aux == 2) exec_gather<D, 2, S, V, MAXD, WIDE>(P, err, I, st, ts);
-            else if (aux == 3) exec_gather<D, 3, S, V, MAXD, WIDE>(P, err, I, st, ts);
+            if (aux == 1) exec_gather<D, 1, S, V, MAXD, WIDE, MAXR>(P, err, I, st, ts);
+            else if (aux == 2) exec_gather<D, 2, S, V, MAXD, WIDE, MAXR>(P, err, I, st, ts);
+            else if (aux == 3) exec_gather<D, 3, S, V, MAXD, WIDE, MAXR>(P, err, I, st, ts);
             break;
         case OPC_FOLD_BEGIN:  // let mut s = init;  (the closure of rows().map(..))
             if constexpr (D < MAXD) {
 #pragma unroll
                 for (int l = 0; l < V; ++l) st[D][l] = (S)I.imm;
 #pragma unroll
-                for (int a = 0; a < kMaxRank; ++a)
+                for (int a = 0; a < MAXR; ++a)
                     if (a >= P.rank) ts.c[a] = 0;
                 ts.red_k = 0;
                 if (P.red_count == 0) next = I.slot;  // empty row: skip the body and its FOLD_STEP
@@ -566,7 +579,7 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
                 }
                 bool carry = true;  // advance the reduction coordinates, last axis fastest
 #pragma unroll
-                for (int a = kMaxRank - 1; a >= 0; --a) {
+                for (int a = MAXR - 1; a >= 0; --a) {
                     if (carry && a >= P.rank && a < P.rank + P.red_rank) {
                         ts.c[a] += 1;
                         if ((uint64_t)ts.c[a] == P.length[a]) ts.c[a] = 0; else carry = false;
@@ -588,44 +601,43 @@ struct SigInstr { uint8_t opc, dtype, op, aux; };
 
 struct NoSig { static constexpr int n = 0; };
 
-template <class Sig, int PC, int D, class S, int V, int MAXD, bool WIDE>
-MDIM_FN void run_static(const Program& P, ErrWord* err, S (&st)[MAXD][V], ThreadState<WIDE>& ts) {
+template <class Sig, int PC, int D, class S, int V, int MAXD, bool WIDE, int MAXR>
+MDIM_FN void run_static(const Program& P, ErrWord* err, S (&st)[MAXD][V], ThreadState<WIDE, MAXR>& ts) {
     if constexpr (PC < Sig::n) {
         constexpr SigInstr I = Sig::code[PC];
-        exec_instr<D, S, V, MAXD, WIDE>(P, err, I.opc, I.dtype, I.op, I.aux, PC, st, ts);
+        exec_instr<D, S, V, MAXD, WIDE, MAXR>(P, err, I.opc, I.dtype, I.op, I.aux, PC, st, ts);
         constexpr int ND = D + (I.opc == OPC_LEAF_VEC || I.opc == OPC_LEAF_BCAST || I.opc == OPC_LEAF_STRIDED || I.opc == OPC_IOTA ||
                                         I.opc == OPC_CONST ? 1
                                 : I.opc == OPC_BINARY ? -1
                                 : I.opc == OPC_GATHER ? 1 - (int)I.aux
                                                       : 0);
-        run_static<Sig, PC + 1, ND, S, V, MAXD, WIDE>(P, err, st, ts);
+        run_static<Sig, PC + 1, ND, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
     }
 }
 
-template <int D, class S, int V, int MAXD, bool WIDE>
-MDIM_FN int interp_step(const Program& P, ErrWord* err, int depth, const Instr& I, int pc, S (&st)[MAXD][V], ThreadState<WIDE>& ts) {
+template <int D, class S, int V, int MAXD, bool WIDE, int MAXR>
+MDIM_FN int interp_step(const Program& P, ErrWord* err, int depth, const Instr& I, int pc, S (&st)[MAXD][V], ThreadState<WIDE, MAXR>& ts) {
     if constexpr (D > MAXD) {
         return P.n_instr;  // unreachable: the planner bounds the depth
     } else {
-        if (depth == D) return exec_instr<D, S, V, MAXD, WIDE>(P, err, I.opc, I.dtype, I.op, I.aux, pc, st, ts);
-        return interp_step<D + 1, S, V, MAXD, WIDE>(P, err, depth, I, pc, st, ts);
+        if (depth == D) return exec_instr<D, S, V, MAXD, WIDE, MAXR>(P, err, I.opc, I.dtype, I.op, I.aux, pc, st, ts);
+        return interp_step<D + 1, S, V, MAXD, WIDE, MAXR>(P, err, depth, I, pc, st, ts);
     }
 }
 
-template <class S, int V, int MAXD, bool WIDE>
-MDIM_FN void run_interp(const Program& P, ErrWord* err, S (&st)[MAXD][V], ThreadState<WIDE>& ts) {
+template <class S, int V, int MAXD, bool WIDE, int MAXR>
+MDIM_FN void run_interp(const Program& P, ErrWord* err, S (&st)[MAXD][V], ThreadState<WIDE, MAXR>& ts) {
     int pc = 0, depth = 0;
     while (pc < P.n_instr) {
         const Instr& I = P.instr[pc];
         const int d = depth_delta(I.opc, I.aux);
-        pc = interp_step<0, S, V, MAXD, WIDE>(P, err, depth, I, pc, st, ts);
+        pc = interp_step<0, S, V, MAXD, WIDE, MAXR>(P, err, depth, I, pc, st, ts);
         depth += d;
     }
 }
 
 // Fast unsigned division by a run-time constant for n < 2^31 (planner guarantees the range):
-// q = umulhi(n, mul) >> shr.
-// mul == 0 encodes division by 1.
+// q = umulhi(n, mul) >> shr.  mul == 0 encodes division by 1.
 MDIM_FN uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t shr) {
 #if defined(__CUDA_ARCH__)
     return mul ? __umulhi(n, mul) >> shr : n;
@@ -636,37 +648,29 @@ MDIM_FN uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t shr) {
 
 // One output vector: decode (Index::from_usize peels the LAST component first, src/index.rs:116-120,
 // src/lib.rs:38-39), evaluate, store at its to_usize position (row-major, src/index.rs:109-114).
-template <class Sig, class S, int V, int MAXD, bool WIDE, bool R1>
+// dec_len[a] is the decode length of axis a (the innermost output axis counted in vectors, 1 for
+// reduction / unused axes) and dec_scale[a] turns the decoded count back into an element coordinate.
+template <class Sig, class S, int V, int MAXD, bool WIDE, int MAXR>
 MDIM_FN void eval_vector(const Program& P, void* out, ErrWord* err, uint64_t g) {
     using coord_t = typename CoordTraits<WIDE>::coord_t;
-    ThreadState<WIDE> ts;
+    ThreadState<WIDE, MAXR> ts;
     ts.pos0 = g * (uint64_t)V;
     ts.mask = (1u << V) - 1u;
     ts.red_k = 0;
+    coord_t rem = (coord_t)g;
 #pragma unroll
-    for (int a = 0; a < kMaxRank; ++a) ts.c[a] = 0;
-    if constexpr (R1) {
-        ts.c[0] = (coord_t)(g * (uint64_t)V);
-    } else {
-        coord_t rem = (coord_t)g;
-#pragma unroll
-        for (int a = kMaxRank - 1; a >= 1; --a) {
-            if (a < P.rank) {
-                const bool inner = (a == P.rank - 1);
-                const uint64_t len = inner ? P.length[a] / (uint64_t)V : P.length[a];
-                coord_t q;
-                if constexpr (WIDE) q = rem / (coord_t)len;
-                else q = fast_div(rem, P.div_mul[a], P.div_shr[a]);
-                const coord_t r = rem - q * (coord_t)len;
-                ts.c[a] = inner ? r * (coord_t)V : r;  // element coordinate of lane 0
-                rem = q;
-            }
-        }
-        ts.c[0] = P.rank <= 1 ? rem * (coord_t)V : rem;
+    for (int a = MAXR - 1; a >= 1; --a) {
+        coord_t q;
+        if constexpr (WIDE) q = rem / (coord_t)P.dec_len[a];
+        else q = fast_div(rem, P.div_mul[a], P.div_shr[a]);
+        const coord_t r = rem - q * (coord_t)P.dec_len[a];
+        ts.c[a] = r * (coord_t)P.dec_scale[a];
+        rem = q;
     }
+    ts.c[0] = rem * (coord_t)P.dec_scale[0];
     S st[MAXD][V];
-    if constexpr (Sig::n > 0) run_static<Sig, 0, 0, S, V, MAXD, WIDE>(P, err, st, ts);
-    else run_interp<S, V, MAXD, WIDE>(P, err, st, ts);
+    if constexpr (Sig::n > 0) run_static<Sig, 0, 0, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
+    else run_interp<S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
     st_vector<S, V>(out, ts.pos0, esize_of(P.out_dtype), st[0], true);
 }
 

@@ -7,8 +7,8 @@ namespace mdim {
 template <class Sig> constexpr const SigInstr* sig_code() { if constexpr (Sig::n > 0) return Sig::code; else return nullptr; }
 
 static const EvalVariant kVariants[] = {
-#define X(Sig, S, V, MAXD, WIDE, R1) \
-    {#Sig, (int)sizeof(S), V, MAXD, WIDE ? 1 : 0, R1 ? 1 : 0, sig_code<Sig>(), Sig::n, &k_eval<Sig, S, V, MAXD, WIDE, R1>},
+#define X(Sig, S, V, MAXD, WIDE, MAXR) \
+    {#Sig, (int)sizeof(S), V, MAXD, WIDE ? 1 : 0, MAXR, sig_code<Sig>(), Sig::n, &k_eval<Sig, S, V, MAXD, WIDE, MAXR>},
 #include "variants_s32.inc"
 #undef X
 };

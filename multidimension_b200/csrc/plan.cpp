@@ -259,6 +259,7 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
         A.ptr = n.data;
         A.offset = n.offset;
         for (int g = 0; g < kMaxRank; ++g) A.stride[g] = g < n_axes ? cstride[ni][g] : 0;
+        A.inner = rank > 0 ? A.stride[rank - 1] : 0;
         *slot = P.n_addr++;
         return MDIM_OK;
     };
@@ -279,6 +280,8 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
                 opc = ok ? OPC_LEAF_VEC : OPC_LEAF_STRIDED;
             } else opc = OPC_LEAF_STRIDED;
             in.opc = (uint8_t)opc; in.slot = (uint16_t)slot;
+            if (opc == OPC_LEAF_VEC)  // re-read along a broadcast output axis => worth keeping in L1
+                for (int g = 0; g < rank; ++g) if (A.stride[g] == 0 && len[g] > 1) in.aux = 1;
             return push_instr(in);
         }
         case MDIM_NODE_IOTA: {
@@ -311,9 +314,14 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
             int own_n = 0;
             for (int p = 0; p < n.n_comp; ++p) {
                 Pred pr;
-                pr.a = axis_map[n.axis_a[p]];
-                pr.b = n.axis_b[p] >= 0 ? axis_map[n.axis_b[p]] : -1;
-                pr.c = n.axis_b[p] >= 0 ? 0 : n.axis_c[p];
+                memset(&pr, 0, sizeof pr);
+                const int a = axis_map[n.axis_a[p]];
+                const int b = n.axis_b[p] >= 0 ? axis_map[n.axis_b[p]] : -1;
+                pr.coef[a] += 1;
+                if (b >= 0) pr.coef[b] -= 1;
+                else if (n.axis_c[p] >= len[a]) { pr.coef[a] = 0; pr.rhs = 1; }  // never on the diagonal
+                else pr.rhs = (int64_t)n.axis_c[p];
+                pr.lane_coef = rank > 0 ? pr.coef[rank - 1] : 0;
                 P.pred[P.n_pred++] = pr; own_n++;
             }
             const bool lazy = has_err_source[child[ni][0]];
@@ -421,11 +429,22 @@ int Builder::emit() {
             for (int g = 0; g < n_axes; ++g)
                 if (cstride[i][g] > INT32_MAX || cstride[i][g] < INT32_MIN) wide = true;
     }
+    // ... and every operand's linear offset must fit in int32 for every coordinate
+    for (int i = 0; i < e->n_nodes; ++i) {
+        const int k = e->nodes[i].kind;
+        if (k != MDIM_NODE_LEAF && k != MDIM_NODE_IOTA && k != MDIM_NODE_GATHER) continue;
+        double reach = (double)(e->nodes[i].offset < 0 ? -e->nodes[i].offset : e->nodes[i].offset);
+        for (int g = 0; g < n_axes; ++g) reach += (double)(len[g] ? len[g] - 1 : 0) * (double)(cstride[i][g] < 0 ? -cstride[i][g] : cstride[i][g]);
+        if (reach >= 2147483647.0) wide = true;
+    }
     plan->wide = wide ? 1 : 0;
-    for (int g = 0; g < rank; ++g) {
-        const uint64_t L = (g == rank - 1) ? len[g] / (uint64_t)V : len[g];
+    plan->n_axes = n_axes;
+    for (int g = 0; g < kMaxRank; ++g) {
+        uint64_t L = 1;
+        if (g < rank) L = (g == rank - 1) ? len[g] / (uint64_t)V : len[g];
+        P.dec_len[g] = L;
+        P.dec_scale[g] = (g == rank - 1) ? (uint32_t)V : 1u;
         find_divisor((uint32_t)std::min<uint64_t>(L, 0x7fffffffull), &P.div_mul[g], &P.div_shr[g]);
-        if (L == 1) { P.div_mul[g] = 0; P.div_shr[g] = 0; }
     }
     depth = 0; max_depth = 0;
     int st = gen(root, 0, 0);
@@ -473,7 +492,8 @@ int Builder::detect_fast_paths() {
                 T.batch_out_stride[T.n_batch] = ostride[g];
                 T.n_batch++;
             }
-            T.tiles_a = (T.len_a + 63) / 64; T.tiles_b = (T.len_b + 63) / 64;
+            const uint64_t tile_a = 256 / (uint64_t)es;  // 16 chunks of 16 bytes along A (k_transpose: TA)
+            T.tiles_a = (T.len_a + tile_a - 1) / tile_a; T.tiles_b = (T.len_b + 63) / 64;
             uint64_t nb = 1; for (int b = 0; b < T.n_batch; ++b) nb *= T.batch_len[b];
             T.n_tiles = T.tiles_a * T.tiles_b * nb;
             plan->kind = KK_TRANSPOSE;

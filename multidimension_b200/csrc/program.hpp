@@ -40,7 +40,8 @@ struct Instr {  // 16 bytes
     uint8_t opc;
     uint8_t dtype;  // result dtype (mdim_dtype)
     uint8_t op;     // mdim_binary_op / mdim_unary_op
-    uint8_t aux;    // UNARY: source dtype; BINARY/FOLD_STEP: rhs dtype; GATHER: n_comp
+    uint8_t aux;    // UNARY: source dtype; BINARY/FOLD_STEP: rhs dtype; GATHER: n_comp;
+                    // LEAF_VEC: 1 = the operand is re-read (broadcast along some axis): allocate in L1
     uint16_t slot;  // LEAF/IOTA/GATHER: addr index; MASK/SELECT: first pred; FOLD_STEP: loop pc
     uint16_t n;     // MASK/SELECT: pred count; BINARY/GATHER/FOLD_STEP: source node (error reports)
     uint64_t imm;   // CONST value bits; SELECT zero; FOLD_BEGIN init
@@ -50,15 +51,17 @@ struct Addr {
     const void* ptr;
     int64_t offset;             // elements
     int64_t stride[kMaxRank];   // elements per unit of each (coalesced) iteration axis
+    int64_t inner;              // stride along the innermost OUTPUT axis (the vector axis)
     int64_t gstride[kMaxComp];  // GATHER: elements per unit of index component
     uint64_t bound[kMaxComp];   // GATHER: size of index component
     int32_t n_peers;            // GATHER over peer-mapped shards (see mdim_node.n_peers)
     int32_t pad;
 };
 
-struct Pred {  // coord[a] == (b >= 0 ? coord[b] : c)
-    int32_t a, b;
-    uint64_t c;
+struct Pred {  // sum_a coef[a] * coord[a] (+ lane * lane_coef) == rhs
+    int32_t coef[kMaxRank];
+    int32_t lane_coef, pad;  // coef of the innermost output axis
+    int64_t rhs;
 };
 
 struct PeerTab {
@@ -78,8 +81,10 @@ struct Program {
     int32_t vec;  // lanes per thread along the innermost output axis
     uint32_t flags;
     uint64_t length[kMaxRank];  // coalesced lengths: out axes then reduction axes (elements)
-    uint32_t div_mul[kMaxRank]; // magic multiplier/shift for the decode of out axis a, where the
-    uint32_t div_shr[kMaxRank]; // innermost out axis is counted in vectors (length/vec)
+    uint64_t dec_len[kMaxRank];   // decode length of axis a: innermost out axis in vectors; 1 if not an out axis
+    uint32_t dec_scale[kMaxRank]; // vec for the innermost out axis, else 1
+    uint32_t div_mul[kMaxRank];   // magic multiplier/shift for division by dec_len[a] (32-bit path)
+    uint32_t div_shr[kMaxRank];
     uint64_t n_vec;             // total output vectors = prod(out lengths) / vec
     uint64_t red_count;         // prod(reduction lengths)
     uint64_t explain_pos;       // PF_EXPLAIN: output position whose failure details to record
@@ -144,6 +149,7 @@ struct Plan {
     int32_t slot_bytes;  // 4 or 8: width of the value-stack slots
     int32_t vec;
     int32_t wide;        // 64-bit coordinates/strides
+    int32_t n_axes;      // rank + red_rank after canonicalisation (selects the MAXR instantiation)
     int32_t max_depth;
     int32_t static_id;   // index into the signature registry, -1 = interpreted
     uint64_t out_elems;

@@ -13,15 +13,25 @@
 namespace mdim {
 int find_static_signature(const char*, int, int, int) { return -1; }
 
-template <class S, int V, int MAXD, bool WIDE>
+template <class S, int V, int MAXD, bool WIDE, int MAXR>
 static void run_all(const Program& P, void* out, ErrWord* err, uint64_t g0, uint64_t g1) {
-    for (uint64_t g = g0; g < g1; ++g) eval_vector<NoSig, S, V, MAXD, WIDE, false>(P, out, err, g);
+    for (uint64_t g = g0; g < g1; ++g) eval_vector<NoSig, S, V, MAXD, WIDE, MAXR>(P, out, err, g);
+}
+
+// the same MAXR choices the device registry offers (variants_s32.inc / variants_s64.inc), plus the
+// stream form MAXR = 1 that the static signatures use
+template <class S, int V, int MAXD, bool WIDE>
+static void run_r(const Plan& p, const Program& P, void* out, ErrWord* err, uint64_t g0, uint64_t g1) {
+    const int need = p.kind == KK_STREAM ? 1 : (p.n_axes < 1 ? 1 : p.n_axes);
+    if (need <= 1) run_all<S, V, MAXD, WIDE, 1>(P, out, err, g0, g1);
+    else if (need <= 3) run_all<S, V, MAXD, WIDE, 3>(P, out, err, g0, g1);
+    else run_all<S, V, MAXD, WIDE, 8>(P, out, err, g0, g1);
 }
 
 template <class S, int V, int MAXD>
 static void run_w(const Plan& p, const Program& P, void* out, ErrWord* err, uint64_t g0, uint64_t g1) {
-    if (p.wide) run_all<S, V, MAXD, true>(P, out, err, g0, g1);
-    else run_all<S, V, MAXD, false>(P, out, err, g0, g1);
+    if (p.wide) run_r<S, V, MAXD, true>(p, P, out, err, g0, g1);
+    else run_r<S, V, MAXD, false>(p, P, out, err, g0, g1);
 }
 
 static int run(const Plan& p, const Program& P, void* out, ErrWord* err, uint64_t g0, uint64_t g1) {

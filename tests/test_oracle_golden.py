@@ -216,3 +216,13 @@ def test_fold_rows_sequential_order():
     a = Array.new((usize, usize), (2, 3), [1, 2, 3, 4, 5, 6])
     trace = R.fold_rows(a, usize, usize, lambda s, x: s * 10 + x, 0).collect()
     assert trace.as_ref() == [123, 456]
+
+
+def test_product_library_is_fresh():
+    """The in-tree .so must be newer than every source it is built from (stale builds hide fixes)."""
+    import glob, os
+    from multidimension_b200 import LIB_PATH
+    assert os.path.exists(LIB_PATH), "run __graft_entry__.build()"
+    src = glob.glob(os.path.join(os.path.dirname(LIB_PATH), "csrc", "*.*")) + [os.path.join(os.path.dirname(LIB_PATH), "..", "include", "mdim.h")]
+    newest = max(os.path.getmtime(p) for p in src if not p.endswith(".log"))
+    assert os.path.getmtime(LIB_PATH) >= newest, "libmdim_b200.so is older than its sources: run __graft_entry__.build()"
