@@ -108,29 +108,64 @@ class ClockSampler:
 
 # ---- the CPU restatement (reference arm and cpu_baseline) -----------------------------------------------
 def cpu_oracle_pass(n, repeat, seed=1):
-    """Time `repeat` single-threaded oracle collects of config 2 over an n-element sample.
-    Returns (seconds per pass, algorithmic bytes per pass)."""
-    from helpers import oracle_lib
-    import multidimension_b200 as P
-    from multidimension_b200 import lowering as L
-    from multidimension_b200.view import _flat
+    """Time `repeat` single-threaded passes of config 2 over an n-element sample through
+    oracle/ref_shaped.c (the collect() loop as rustc would monomorphise it: bounds asserts, push with
+    capacity check, separately rounded mul/add, no SIMD).  Returns (seconds per pass, algorithmic bytes)."""
+    from helpers import refshaped_lib
     rng = np.random.default_rng(seed)
-    a = P.Array.new(P.usize, n, rng.uniform(-1, 1, n).astype(np.float32))
-    b = P.Array.new(P.usize, n, rng.uniform(-1, 1, n).astype(np.float32))
-    view = a.zip(b).map(lambda p: p[0] * p[1] + np.float32(1))
-    groups, value = view._lower()
-    em = L.emit(value, _flat(groups), "host")
+    a = rng.uniform(-1, 1, n).astype(np.float32)
+    b = rng.uniform(-1, 1, n).astype(np.float32)
     out = np.empty(n, dtype=np.float32)
-    lib = oracle_lib()
+    lib = refshaped_lib()
     times = []
     for _ in range(repeat):
         t0 = time.perf_counter()
-        st = lib.mdim_oracle_collect(C.byref(em.expr), out.ctypes.data, None)
+        st = lib.ref_c2_zip_map(a.ctypes.data, b.ctypes.data, n, out.ctypes.data)
         times.append(time.perf_counter() - t0)
         assert st == 0
-    want = a.as_ref() * b.as_ref() + np.float32(1)
+    want = a * b + np.float32(1)
     assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
     return times, 12 * n
+
+
+def cpu_ops_table():
+    """The other configs on one host core (bounded samples), GB/s on algorithmic bytes."""
+    from helpers import refshaped_lib
+    lib = refshaped_lib()
+    rng = np.random.default_rng(2)
+    out = {}
+
+    def timed(fn, nbytes, sample):
+        t0 = time.perf_counter()
+        assert fn() == 0
+        dt = time.perf_counter() - t0
+        return {"GB/s": round(nbytes / dt / 1e9, 3), "sample": sample}
+    m = 4096
+    a = rng.uniform(-1, 1, m * m).astype(np.float32)
+    o = np.empty(m * m, np.float32)
+    out["c1_transpose_4096x4096_f32"] = timed(lambda: lib.ref_c1_transpose(a.ctypes.data, m, m, o.ctypes.data), 8 * m * m, "full size")
+    n3, m3 = 1 << 24, 1 << 28
+    src = rng.uniform(-1, 1, m3).astype(np.float32)
+    idx = rng.integers(0, m3, n3).astype(np.uint64)
+    o3 = np.empty(n3, np.float32)
+    out["c3_compose_gather"] = timed(lambda: lib.ref_c3_compose(idx.ctypes.data, n3, src.ctypes.data, m3, o3.ctypes.data), 16 * n3,
+                                     "2^24 indices into a 2^28-element source (full: 2^28 into 2^30)")
+    I, J, K = 256, 256, 256
+    a4 = src[: I * J * K]
+    sums = np.empty(I * J, np.float32)
+    out["c4a_fold_sum_last_axis"] = timed(lambda: lib.ref_c4_fold(a4.ctypes.data, I, J, K, sums.ctypes.data), 4 * I * J * K + 4 * I * J,
+                                          "(256,256,256) of (1024,1024,256)")
+    mean = (sums / np.float32(K)).astype(np.float32)
+    o4 = np.empty(I * J * K, np.float32)
+    out["c4b_broadcast_subtract"] = timed(lambda: lib.ref_c4_sub(a4.ctypes.data, mean.ctypes.data, I, J, K, o4.ctypes.data), 8 * I * J * K + 4 * I * J,
+                                          "(256,256,256) of (1024,1024,256)")
+    P_, Q, R = 16, 16, 64
+    a5 = src[: P_ * Q]
+    w5 = src[1000: 1000 + R]
+    o5 = np.empty(Q * P_ * Q * P_ * R, np.float32)
+    out["c5_rank5_chain"] = timed(lambda: lib.ref_c5_chain(a5.ctypes.data, P_, Q, w5.ctypes.data, R, o5.ctypes.data), 4 * o5.size,
+                                  "P=Q=16, R=64 (2^22 outputs) of P=Q=R=64 (2^30)")
+    return out
 
 
 def pin_to_one_core():
@@ -145,7 +180,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     pin_to_one_core()
-    n = 1 << 24  # bounded sample: 2^24 of the 2^30 elements per step
+    n = 1 << 26  # bounded sample: 2^26 of the 2^30 elements per step
     times, nbytes = cpu_oracle_pass(n, args.warmup + args.steps)
     timed = times[args.warmup:]
     sec = sum(timed) / len(timed)
@@ -155,7 +190,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample,
-                   "note": "CPU restatement of the reference's single-threaded collect() (oracle/mdim_oracle.c); the Rust crate cannot be built in this image"},
+                   "note": "CPU restatement of the reference's single-threaded collect() as monomorphic loops (oracle/ref_shaped.c); the Rust crate cannot be built in this image"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -305,12 +340,13 @@ def main():
     # ---- CPU restatement beside it (rank 0, N=1) -----------------------------------------------------------------------------------
     if not args.no_cpu and world == 1 and rank == 0:
         pin_to_one_core()
-        sample_n = 1 << 26
+        sample_n = 1 << 28
         times, nbytes = cpu_oracle_pass(sample_n, 2)
         result["cpu_baseline"] = {"value": nbytes / min(times) / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
                                   "sample": f"{sample_n} of {N_ELEMS} elements of config 2, 2 passes (best), single thread; "
-                                            f"oracle/mdim_oracle.c restates the reference's collect() (no Rust toolchain in this image)",
-                                  "host_cores_available": os.cpu_count()}
+                                            f"oracle/ref_shaped.c restates the reference's collect() loop (no Rust toolchain in this image; "
+                                            f"the reference is single-threaded by construction)",
+                                  "host_cores_available": os.cpu_count(), "ops": cpu_ops_table()}
 
     if rank == 0:
         print(json.dumps(result))

@@ -72,158 +72,209 @@ __device__ __forceinline__ uint32_t apply_any(int dtype, int op, uint32_t a, uin
 }
 
 constexpr int kRowsPerTile = 32;  // one row per lane
+constexpr int kBarBytes = 512;     // mbarriers ahead of the tiles: 8 warps x up to 8 stages x 8 B
 
+// Work is cut into ITEMS: (block of 32 rows) x (chunk of `ch` columns), column chunks of one row block
+// consecutive, so a lane's accumulator simply carries over from chunk to chunk.  Each warp owns a ring
+// of `stages` shared-memory tiles [32][ch] (dense, no padding) and walks its items in order:
+//   fill   : when ch == row_len the 32 rows are one contiguous run of global memory — ONE
+//            cp.async.bulk (TMA) of up to 64 KB issued by lane 0; otherwise each lane issues the bulk copy
+//            of its own row piece (32 copies in flight at once).  Completion is counted in bytes on
+//            the tile's mbarrier.
+//   fold   : lane l walks row l with 16-byte shared loads and a dependent chain of adds — strictly left
+//            to right.  Lanes start `skew * (l & 7)` steps late, which makes the 8 lanes of each
+//            quarter-warp hit 8 different 16-byte bank groups of the dense tile (no padding needed).
+//   finish : after the last chunk, either lane l stores fold[l] (fold only), or (ch == row_len) the warp
+//            re-reads the tile row by row and writes  x (eop) g(fold[row])  with coalesced 16-byte
+//            streaming stores (BASELINE config 4: the input is read from HBM exactly once).
 // FAST = f32 with fold op ADD and epilogue op SUB (or none): the shape of BASELINE config 4.
-template <bool FAST, bool TMA>
+template <bool FAST>
 __global__ void __launch_bounds__(kFoldThreads)
-k_fold_rows(const __grid_constant__ FoldRowsPlan R, void* __restrict__ out_v, int n_warps, int stages, int pitch) {
+k_fold_rows(const __grid_constant__ FoldRowsPlan R, void* __restrict__ out_v, int n_warps, int stages, int ch, int skew, uint32_t q4_mul,
+            uint32_t q4_shr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp >= n_warps) return;
-    const uint32_t tile_words = (uint32_t)kRowsPerTile * (uint32_t)pitch;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [n_warps][stages], 8 B each (<= 128 B)
-    uint32_t* tiles = reinterpret_cast<uint32_t*>(smem_raw + 128) + (size_t)warp * stages * tile_words;
+    const uint32_t tile_words = (uint32_t)kRowsPerTile * (uint32_t)ch;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [n_warps][stages], 8 B each (<= kBarBytes)
+    uint32_t* tiles = reinterpret_cast<uint32_t*>(smem_raw + kBarBytes) + (size_t)warp * stages * tile_words;
     uint64_t* my_bars = bars + warp * stages;
 
-    const uint32_t row_len = R.row_len, q4 = row_len >> 2, row_bytes = row_len * 4u;
+    const uint32_t row_len = R.row_len, row_bytes = row_len * 4u;
+    const uint32_t n_chunks = (row_len + (uint32_t)ch - 1) / (uint32_t)ch;
+    const bool dense = n_chunks == 1;
     const char* __restrict__ src = (const char*)R.src + R.src_offset * 4;
-    const uint64_t n_tiles = (R.n_rows + kRowsPerTile - 1) / kRowsPerTile;
+    const uint64_t n_blocks = (R.n_rows + kRowsPerTile - 1) / kRowsPerTile;
     const uint64_t total_warps = (uint64_t)gridDim.x * n_warps;
     const uint64_t gw = (uint64_t)blockIdx.x * n_warps + warp;
+    // this warp's row blocks: gw, gw + total_warps, ...; its items: those blocks x n_chunks, in order
+    const uint64_t my_blocks = gw < n_blocks ? (n_blocks - gw + total_warps - 1) / total_warps : 0;
+    const uint64_t my_items = my_blocks * n_chunks;
 
-    auto issue = [&](uint64_t tile, int s) {  // lane 0 only
-        const uint64_t row0 = tile * kRowsPerTile;
+    auto fill = [&](uint64_t item) {  // whole warp
+        const int s = (int)(item % (uint64_t)stages);
+        const uint64_t blk = gw + (item / n_chunks) * total_warps;
+        const uint32_t c = (uint32_t)(item % n_chunks);
+        const uint64_t row0 = blk * kRowsPerTile;
         const uint32_t nrows = (uint32_t)min((uint64_t)kRowsPerTile, R.n_rows - row0);
-        mbar_expect_tx(&my_bars[s], nrows * row_bytes);
+        const uint32_t cols = min((uint32_t)ch, row_len - c * (uint32_t)ch);
         uint32_t* dst = tiles + (size_t)s * tile_words;
-        for (uint32_t r = 0; r < nrows; ++r) tma_load_1d(dst + r * pitch, src + (row0 + r) * (uint64_t)row_bytes, row_bytes, &my_bars[s]);
+        if (lane == 0) mbar_expect_tx(&my_bars[s], nrows * cols * 4u);
+        __syncwarp();
+        if (dense) {
+            if (lane == 0) tma_load_1d(dst, src + row0 * (uint64_t)row_bytes, nrows * row_bytes, &my_bars[s]);
+        } else if ((uint32_t)lane < nrows) {
+            tma_load_1d(dst + lane * ch, src + (row0 + lane) * (uint64_t)row_bytes + (uint64_t)c * ch * 4u, cols * 4u, &my_bars[s]);
+        }
     };
 
-    if constexpr (TMA) {
-        if (lane == 0) {
-            for (int s = 0; s < stages; ++s) mbar_init(&my_bars[s], 1);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the inits visible to the TMA unit
-        }
-        __syncwarp();
-        if (lane == 0)
-            for (int s = 0; s < stages; ++s) {
-                const uint64_t t = gw + (uint64_t)s * total_warps;
-                if (t < n_tiles) issue(t, s);
-            }
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&my_bars[s], 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the inits visible to the TMA unit
     }
+    __syncwarp();
+    for (uint64_t it = 0; it < (uint64_t)stages && it < my_items; ++it) fill(it);
 
-    uint64_t it = 0;
-    for (uint64_t tile = gw; tile < n_tiles; tile += total_warps, ++it) {
+    const int my_skew = skew * (lane & 7);
+    uint32_t fold = (uint32_t)R.init;
+    for (uint64_t it = 0; it < my_items; ++it) {
         const int s = (int)(it % (uint64_t)stages);
         const uint32_t parity = (uint32_t)((it / (uint64_t)stages) & 1u);
-        const uint64_t row0 = tile * kRowsPerTile;
+        const uint64_t blk = gw + (it / n_chunks) * total_warps;
+        const uint32_t c = (uint32_t)(it % n_chunks);
+        const uint64_t row0 = blk * kRowsPerTile;
         const uint32_t nrows = (uint32_t)min((uint64_t)kRowsPerTile, R.n_rows - row0);
+        const uint32_t cols = min((uint32_t)ch, row_len - c * (uint32_t)ch);
+        const int q4 = (int)(cols >> 2);
         uint32_t* tile_s = tiles + (size_t)s * tile_words;
+        if (c == 0) fold = (uint32_t)R.init;
+        mbar_wait(&my_bars[s], parity);
 
-        if constexpr (TMA) {
-            mbar_wait(&my_bars[s], parity);
-        } else {
-            // synchronous fallback: the warp copies its tile with 128-bit loads/stores
-            for (uint32_t r = 0; r < nrows; ++r)
-                for (uint32_t c = lane; c < q4; c += 32) {
-                    uint4 v;
-                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + (row0 + r) * (uint64_t)row_bytes + c * 16u));
-                    *reinterpret_cast<uint4*>(tile_s + r * pitch + c * 4) = v;
-                }
-            __syncwarp();
-        }
-
-        // ---- sum: lane l folds row l, strictly left to right --------------------------------------
-        uint32_t fold = (uint32_t)R.init;
-        if ((uint32_t)lane < nrows) {
-            const uint4* rowp = reinterpret_cast<const uint4*>(tile_s + lane * pitch);
+        // ---- fold: lane l folds row l, strictly left to right ------------------------------------------
+        {
+            const uint4* rowp = reinterpret_cast<const uint4*>(tile_s + lane * ch);
+            const bool live = (uint32_t)lane < nrows;
+            const int steps = q4 + 7 * skew;
             if constexpr (FAST) {
                 float acc = __uint_as_float(fold);
-#pragma unroll 4
-                for (uint32_t k = 0; k < q4; ++k) {
-                    const uint4 v = rowp[k];
-                    acc = __fadd_rn(acc, __uint_as_float(v.x));
-                    acc = __fadd_rn(acc, __uint_as_float(v.y));
-                    acc = __fadd_rn(acc, __uint_as_float(v.z));
-                    acc = __fadd_rn(acc, __uint_as_float(v.w));
+                for (int t0 = 0; t0 < steps; t0 += 4) {  // 4 shared loads in flight ahead of the dependent add chain
+                    uint4 v[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = t0 + j - my_skew;
+                        ok[j] = live && k >= 0 && k < q4;
+                        if (ok[j]) v[j] = rowp[k];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (ok[j]) {  // never add a padding zero: -0.0 + 0.0 would flip the sign
+                            acc = __fadd_rn(acc, __uint_as_float(v[j].x));
+                            acc = __fadd_rn(acc, __uint_as_float(v[j].y));
+                            acc = __fadd_rn(acc, __uint_as_float(v[j].z));
+                            acc = __fadd_rn(acc, __uint_as_float(v[j].w));
+                        }
+                    }
                 }
                 fold = __float_as_uint(acc);
             } else {
-                for (uint32_t k = 0; k < q4; ++k) {
-                    const uint4 v = rowp[k];
-                    fold = apply_any(R.dtype, R.op, fold, v.x);
-                    fold = apply_any(R.dtype, R.op, fold, v.y);
-                    fold = apply_any(R.dtype, R.op, fold, v.z);
-                    fold = apply_any(R.dtype, R.op, fold, v.w);
+                for (int t = 0; t < steps; ++t) {
+                    const int k = t - my_skew;
+                    if (live && k >= 0 && k < q4) {
+                        const uint4 v = rowp[k];
+                        fold = apply_any(R.dtype, R.op, fold, v.x);
+                        fold = apply_any(R.dtype, R.op, fold, v.y);
+                        fold = apply_any(R.dtype, R.op, fold, v.z);
+                        fold = apply_any(R.dtype, R.op, fold, v.w);
+                    }
                 }
             }
         }
-        uint32_t g = fold;
-        if (R.has_post) g = apply_any(R.dtype, R.post_op, g, (uint32_t)R.post_imm);
 
-        if (R.epilogue == 0) {
-            // fold only: one value per row, coalesced 128 B per warp
-            if ((uint32_t)lane < nrows) reinterpret_cast<uint32_t*>(out_v)[row0 + lane] = fold;
-        } else {
-            // out[row][k] = src[row][k] (eop) g[row]; Zip over (I, J) x (I, ()) — the () axis of the
-            // fold is expanded by Broadcast (src/broadcast.rs:54-60), i.e. g is constant along k
-            char* __restrict__ out = (char*)out_v;
-            for (uint32_t r = 0; r < nrows; ++r) {
-                const uint32_t gr = __shfl_sync(0xffffffffu, g, (int)r);
-                const uint4* rowp = reinterpret_cast<const uint4*>(tile_s + r * pitch);
-                char* orow = out + (row0 + r) * (uint64_t)row_bytes;
-                for (uint32_t c = lane; c < q4; c += 32) {
-                    uint4 v = rowp[c];
-                    if constexpr (FAST) {
-                        const float m = __uint_as_float(gr);
-                        v.x = __float_as_uint(__fsub_rn(__uint_as_float(v.x), m));
-                        v.y = __float_as_uint(__fsub_rn(__uint_as_float(v.y), m));
-                        v.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), m));
-                        v.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), m));
-                    } else {
-                        v.x = apply_any(R.dtype, R.eop, v.x, gr);
-                        v.y = apply_any(R.dtype, R.eop, v.y, gr);
-                        v.z = apply_any(R.dtype, R.eop, v.z, gr);
-                        v.w = apply_any(R.dtype, R.eop, v.w, gr);
+        // ---- finish ---------------------------------------------------------------------------------------
+        if (c + 1 == n_chunks) {
+            if (R.epilogue == 0) {
+                // fold only: one value per row, coalesced 128 B per warp
+                if ((uint32_t)lane < nrows) reinterpret_cast<uint32_t*>(out_v)[row0 + lane] = fold;
+            } else {
+                // out[row][k] = src[row][k] (eop) g[row]; Zip over (I, J) x (I, ()) — the () axis of the
+                // fold is expanded by Broadcast (src/broadcast.rs:54-60), i.e. g is constant along k
+                uint32_t g = fold;
+                if (R.has_post) g = apply_any(R.dtype, R.post_op, g, (uint32_t)R.post_imm);
+                // The dense tile [nrows][row_len] is also ONE contiguous run of the output: walk it flat, 512
+                // bytes per warp instruction, each lane fetching its row's g by shuffle.
+                char* __restrict__ obase = (char*)out_v + row0 * (uint64_t)row_bytes;
+                const uint4* tp = reinterpret_cast<const uint4*>(tile_s);
+                const uint32_t n16 = nrows * (uint32_t)q4;
+#pragma unroll 4
+                for (uint32_t i0 = 0; i0 < n16; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    const bool in = i < n16;
+                    const uint32_t row = __umulhi(in ? i : 0u, q4_mul) >> q4_shr;  // i / q4
+                    const uint32_t gr = __shfl_sync(0xffffffffu, g, (int)row);
+                    if (in) {
+                        uint4 v = tp[i];
+                        if constexpr (FAST) {
+                            const float m = __uint_as_float(gr);
+                            v.x = __float_as_uint(__fsub_rn(__uint_as_float(v.x), m));
+                            v.y = __float_as_uint(__fsub_rn(__uint_as_float(v.y), m));
+                            v.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), m));
+                            v.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), m));
+                        } else {
+                            v.x = apply_any(R.dtype, R.eop, v.x, gr);
+                            v.y = apply_any(R.dtype, R.eop, v.y, gr);
+                            v.z = apply_any(R.dtype, R.eop, v.z, gr);
+                            v.w = apply_any(R.dtype, R.eop, v.w, gr);
+                        }
+                        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(obase + (size_t)i * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
                     }
-                    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(orow + c * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
                 }
             }
         }
         __syncwarp();  // every lane is done reading this stage before it is refilled
-        if constexpr (TMA) {
-            const uint64_t next = tile + (uint64_t)stages * total_warps;
-            if (lane == 0 && next < n_tiles) issue(next, s);
-        }
+        if (it + (uint64_t)stages < my_items) fill(it + (uint64_t)stages);
     }
 }
 
 }  // namespace
 
 void launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream_t stream) {
-    // pitch: row_len padded so that pitch/4 is odd (16-byte shared loads of 8 consecutive rows hit
-    // 8 distinct bank groups) and rows stay 16-byte aligned for the bulk copies
-    int pitch = (int)R.row_len;
-    if (((pitch / 4) & 1) == 0) pitch += 4;
-    const size_t tile_bytes = (size_t)kRowsPerTile * pitch * 4;
-    const size_t budget = 200 * 1024;
-    int stages = 2, n_warps = (int)(budget / (tile_bytes * 2));
-    if (n_warps < 1) { stages = 1; n_warps = (int)(budget / tile_bytes); }
-    if (n_warps < 1) n_warps = 1;
-    if (n_warps > kFoldThreads / 32) n_warps = kFoldThreads / 32;
-    const size_t smem = 128 + (size_t)n_warps * stages * tile_bytes;
-    const uint64_t n_tiles = (R.n_rows + kRowsPerTile - 1) / kRowsPerTile;
-    int grid = (int)std::min<uint64_t>((n_tiles + n_warps - 1) / n_warps, (uint64_t)sm_count);
+    static const int env_warps = [] { const char* e = getenv("MDIM_FOLD_WARPS"); return e ? atoi(e) : 0; }();
+    static const int env_stages = [] { const char* e = getenv("MDIM_FOLD_STAGES"); return e ? atoi(e) : 0; }();
+    // column chunk: the whole row when a 32-row tile of it fits 64 KB (and always for the fused form,
+    // which needs the whole row resident); else 256 columns per item
+    int ch = (int)R.row_len;
+    if (R.epilogue == 0 && R.row_len > 512) ch = 256;
+    const size_t tile_bytes = (size_t)kRowsPerTile * ch * 4;
+    const size_t budget = 227 * 1024 - kBarBytes;  // the whole opt-in shared memory of an SM: 7 tiles of 32 KB
+    int max_tiles = (int)(budget / tile_bytes);
+    if (max_tiles < 1) max_tiles = 1;
+    // Measured on B200 (profiles/): warps hide each other's latency better than stages do — six warps with
+    // one tile each beat three warps with two — so fill the warps first, then deepen the rings.
+    const int max_warps = kFoldThreads / 32;
+    int n_warps = env_warps > 0 ? env_warps : std::min(max_warps, max_tiles);
+    if (n_warps > max_warps) n_warps = max_warps;
+    if (n_warps > max_tiles) n_warps = max_tiles;
+    int stages = env_stages > 0 ? env_stages : std::min(8, std::min(4, max_tiles / n_warps));
+    if (stages * n_warps > max_tiles) stages = max_tiles / n_warps;
+    if (stages < 1) stages = 1;
+    const size_t smem = kBarBytes + (size_t)n_warps * stages * tile_bytes;
+    const uint64_t n_blocks = (R.n_rows + kRowsPerTile - 1) / kRowsPerTile;
+    int grid = (int)std::min<uint64_t>((n_blocks + n_warps - 1) / n_warps, (uint64_t)sm_count);
     if (grid < 1) grid = 1;
-    const bool fast = R.dtype == MDIM_F32 && R.op == MDIM_ADD && (R.epilogue == 0 || R.eop == MDIM_SUB);
-    static const bool use_tma = [] { const char* e = getenv("MDIM_FOLD_TMA"); return !(e && e[0] == '0'); }();
+    // bank-conflict-free skew needs the dense row pitch to be a multiple of 8 sixteen-byte chunks
+    const int skew = ((ch / 4) % 8 == 0) ? 1 : 0;
+    const bool fast = R.dtype == MDIM_F32 && R.op == MDIM_ADD && (R.epilogue == 0 || (R.eop == MDIM_SUB));
+    // i / q4 for the flat epilogue walk: umulhi(i, mul) >> shr, exact for i < 2^31 (q4 >= 2 here)
+    uint32_t q4 = (uint32_t)ch / 4, lg = 0;
+    while ((1u << lg) < q4) ++lg;
+    const uint32_t q4_shr = lg - 1 + (q4 == 1 ? 1 : 0);
+    const uint32_t q4_mul = (uint32_t)(((1ull << (31 + lg)) + q4 - 1) / q4);
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, kFoldThreads, smem, stream>>>(R, out, n_warps, stages, pitch);
+        kern<<<grid, kFoldThreads, smem, stream>>>(R, out, n_warps, stages, ch, skew, q4_mul, q4_shr);
     };
-    if (fast) { if (use_tma) go(k_fold_rows<true, true>); else go(k_fold_rows<true, false>); }
-    else { if (use_tma) go(k_fold_rows<false, true>); else go(k_fold_rows<false, false>); }
+    if (fast) go(k_fold_rows<true>); else go(k_fold_rows<false>);
 }
 
 }  // namespace mdim

@@ -47,7 +47,7 @@ int transpose_max_ctas_per_sm();
 // ------------------------------------------------------------------------------------------------
 // K4: sequential-order last-axis fold, optionally fused with a broadcast epilogue (k_fold.cu)
 // ------------------------------------------------------------------------------------------------
-constexpr int kFoldThreads = 128;
+constexpr int kFoldThreads = 256;
 void launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream_t stream);
 
 }  // namespace mdim

@@ -519,7 +519,7 @@ int Builder::detect_fast_paths() {
         };
         // the row kernel has no error channel: integer DIV/REM (which can panic) stay on the evaluator
         auto row_safe = [&](int op) { return op != MDIM_SHL && op != MDIM_SHR && !(is_int(F.dtype) && (op == MDIM_DIV || op == MDIM_REM)); };
-        if (es == 4 && row_len >= 8 && row_len <= 1024 && row_len % 4 == 0 && row_safe(F.op)) {
+        if (es == 4 && row_len >= 8 && row_len <= (1u << 24) && row_len % 4 == 0 && row_safe(F.op)) {
             FoldRowsPlan& R = plan->fr;
             memset(&R, 0, sizeof R);
             R.row_len = (uint32_t)row_len; R.op = F.op; R.dtype = F.dtype; R.init = F.imm.u64 & 0xffffffffull;
@@ -534,7 +534,7 @@ int Builder::detect_fast_paths() {
             // (2b) fused: root = BINARY(eop, LEAF x[r][k], G) with G = FOLD(LEAF x'[r][k']) or
             //      BINARY(post_op, FOLD(..), CONST); out rank 2 = (rows, row_len); x' is the same
             //      buffer addressed (row_len, 0 | 1)
-            if (rank == 2 && N[root].kind == MDIM_NODE_BINARY && len[1] == row_len) {
+            if (rank == 2 && N[root].kind == MDIM_NODE_BINARY && len[1] == row_len && row_len <= 512) {  // fused: whole rows resident in smem
                 const int lx = child[root][0], g = child[root][1];
                 int fnode = -1; bool has_post = false; int post_op = 0; uint64_t post_imm = 0;
                 if (g == fold_node) fnode = g;

@@ -122,3 +122,23 @@ def assert_same_bits(got, want, what=""):
             return
         k = int(bad[0])
         raise AssertionError(f"{what}: {bad.size} of {got.size} elements differ; first at {k}: got {got[k]!r}, want {want[k]!r}")
+
+
+def refshaped_lib():
+    """oracle/ref_shaped.c: the five BASELINE configs as rustc-shaped monomorphic loops (CPU baseline)."""
+    if "ref" not in _libs:
+        path = os.path.join(ORACLE_DIR, "_build", "libmdim_refshaped.so")
+        if not os.path.exists(path):
+            subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
+        lib = C.CDLL(path)
+        P_, U = C.c_void_p, C.c_uint64
+        lib.ref_c2_zip_map.argtypes = [P_, P_, U, P_]
+        lib.ref_c1_transpose.argtypes = [P_, U, U, P_]
+        lib.ref_c3_compose.argtypes = [P_, U, P_, U, P_]
+        lib.ref_c4_fold.argtypes = [P_, U, U, U, P_]
+        lib.ref_c4_sub.argtypes = [P_, P_, U, U, U, P_]
+        lib.ref_c5_chain.argtypes = [P_, U, U, P_, U, P_]
+        for f in ("ref_c2_zip_map", "ref_c1_transpose", "ref_c3_compose", "ref_c4_fold", "ref_c4_sub", "ref_c5_chain"):
+            getattr(lib, f).restype = C.c_int
+        _libs["ref"] = lib
+    return _libs["ref"]
