@@ -87,7 +87,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def start(self):
         if self.nv:
