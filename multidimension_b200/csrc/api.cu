@@ -48,10 +48,12 @@ static bool sig_matches(const EvalVariant& v, const char* sig, int sig_len) {
     return true;
 }
 
-int find_static_signature(const char* sig, int sig_len, int slot_bytes, int vec) {
+int find_static_signature(const char* sig, int sig_len, int slot_bytes, int vec, int vpt, int need_maxr, int wide) {
+    if (wide) return -1;  // signatures are instantiated with 32-bit coordinates only
     const std::vector<EvalVariant>& R = registry();
     for (size_t i = 0; i < R.size(); ++i)
-        if (R[i].slot_bytes == slot_bytes && R[i].vec == vec && sig_matches(R[i], sig, sig_len)) return (int)i;
+        if (R[i].slot_bytes == slot_bytes && R[i].vec == vec && R[i].vpt == vpt && R[i].maxr >= need_maxr && !R[i].wide && sig_matches(R[i], sig, sig_len))
+            return (int)i;
     return -1;
 }
 
@@ -61,13 +63,13 @@ static const EvalVariant* select_variant(const Plan& p, bool force_interp) {
     const EvalVariant* best = nullptr;
     if (p.static_id >= 0 && !p.wide && !force_interp) {
         for (const EvalVariant& v : R) {
-            if (v.slot_bytes != p.slot_bytes || v.vec != p.vec || v.wide || v.maxr < need || !sig_matches(v, p.sig, p.sig_len)) continue;
+            if (v.slot_bytes != p.slot_bytes || v.vec != p.vec || v.vpt != p.vpt || v.wide || v.maxr < need || !sig_matches(v, p.sig, p.sig_len)) continue;
             if (!best || v.maxr < best->maxr) best = &v;
         }
         if (best) return best;
     }
     for (const EvalVariant& v : R) {
-        if (v.sig || v.slot_bytes != p.slot_bytes || v.vec != p.vec || v.wide != p.wide || v.maxr < need || v.max_depth < p.max_depth) continue;
+        if (v.sig || v.slot_bytes != p.slot_bytes || v.vec != p.vec || v.vpt != p.vpt || v.wide != p.wide || v.maxr < need || v.max_depth < p.max_depth) continue;
         if (!best || v.maxr < best->maxr || (v.maxr == best->maxr && v.max_depth < best->max_depth)) best = &v;
     }
     return best;
@@ -153,7 +155,7 @@ bool plan_can_fail(const Plan& p) {
 }
 
 int launch_eval(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err, bool explain, uint64_t explain_pos) {
-    const EvalVariant* v = select_variant(p, explain);
+    const EvalVariant* v = select_variant(p, false);
     if (!v) return set_error(ctx, MDIM_ERR_UNSUPPORTED, "no evaluator instantiation for this expression");
     uint64_t g0 = 0, g1 = p.prog.n_vec;
     int grid;
@@ -161,7 +163,7 @@ int launch_eval(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err, bool expl
         Program q = p.prog;
         q.flags |= PF_EXPLAIN;
         q.explain_pos = explain_pos;
-        g0 = explain_pos / (uint64_t)p.vec;
+        g0 = explain_pos / ((uint64_t)p.vec * (uint64_t)p.vpt);
         g1 = g0 + 1;
         v->fn<<<1, kEvalThreads, 0, ctx->stream>>>(q, out, err, g0, g1);
     } else {

@@ -648,18 +648,19 @@ MDIM_FN uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t shr) {
 
 // One output vector: decode (Index::from_usize peels the LAST component first, src/index.rs:116-120,
 // src/lib.rs:38-39), evaluate, store at its to_usize position (row-major, src/index.rs:109-114).
-// dec_len[a] is the decode length of axis a (the innermost output axis counted in vectors, 1 for
-// reduction / unused axes) and dec_scale[a] turns the decoded count back into an element coordinate.
-template <class Sig, class S, int V, int MAXD, bool WIDE, int MAXR>
+// Program axis 0 is the vector axis, so the decode runs a = 0, 1, ...: dec_len[a] is the decode length
+// of axis a (axis 0 counted in thread trips of V * VPT elements; 1 for reduction / unused axes) and
+// dec_scale[a] turns the decoded count back into an element coordinate.
+template <class Sig, class S, int V, int MAXD, bool WIDE, int MAXR, int VPT>
 MDIM_FN void eval_vector(const Program& P, void* out, ErrWord* err, uint64_t g) {
     using coord_t = typename CoordTraits<WIDE>::coord_t;
     ThreadState<WIDE, MAXR> ts;
-    ts.pos0 = g * (uint64_t)V;
+    ts.pos0 = g * (uint64_t)(V * VPT);
     ts.mask = (1u << V) - 1u;
     ts.red_k = 0;
     coord_t rem = (coord_t)g;
 #pragma unroll
-    for (int a = MAXR - 1; a >= 1; --a) {
+    for (int a = 0; a < MAXR - 1; ++a) {  // axis 0 = the vector axis, peeled first
         coord_t q;
         if constexpr (WIDE) q = rem / (coord_t)P.dec_len[a];
         else q = fast_div(rem, P.div_mul[a], P.div_shr[a]);
@@ -667,11 +668,19 @@ MDIM_FN void eval_vector(const Program& P, void* out, ErrWord* err, uint64_t g) 
         ts.c[a] = r * (coord_t)P.dec_scale[a];
         rem = q;
     }
-    ts.c[0] = rem * (coord_t)P.dec_scale[0];
+    ts.c[MAXR - 1] = rem * (coord_t)P.dec_scale[MAXR - 1];
     S st[MAXD][V];
-    if constexpr (Sig::n > 0) run_static<Sig, 0, 0, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
-    else run_interp<S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
-    st_vector<S, V>(out, ts.pos0, esize_of(P.out_dtype), st[0], true);
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {  // VPT consecutive vectors along the vector axis share one decode
+        if constexpr (Sig::n > 0) run_static<Sig, 0, 0, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
+        else run_interp<S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
+        st_vector<S, V>(out, ts.pos0, esize_of(P.out_dtype), st[0], true);
+        if constexpr (VPT > 1) {
+            ts.c[0] += (coord_t)V;
+            ts.pos0 += (uint64_t)V;
+            ts.mask = (1u << V) - 1u;
+        }
+    }
 }
 
 }  // namespace mdim

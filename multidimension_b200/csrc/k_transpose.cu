@@ -16,6 +16,8 @@
 // 16-byte stores hit 8 distinct chunks, and in the read phase the 32 lanes (8 b-groups x 4 a's)
 // hit 8 distinct chunks x 4 distinct words.
 // Bit-exact by construction (pure data movement).  HBM-bound: algorithmic bytes = 2 x elements.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace mdim {
@@ -119,11 +121,122 @@ __global__ void __launch_bounds__(kTrThreads) k_transpose(const __grid_constant_
     }
 }
 
-void launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t stream) {
+// ---- pipelined form (aligned operands): cp.async multi-stage ring ------------------------------------
+// Same tile geometry and swizzle as above, but the global -> shared leg is `cp.async.cg` (16 bytes per
+// request, straight into its swizzled slot, no registers) issued kStages-1 tiles ahead, so every CTA
+// keeps 32 KB of loads in flight while it drains the current tile; one __syncthreads per tile.
+constexpr int kTrStages = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 16 : 0;  // src-size 0: the slot is zero-filled and the source is not read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(n) : "memory");
+}
+
+template <int ES>
+__global__ void __launch_bounds__(kTrThreads) k_transpose_pipe(const __grid_constant__ TransposePlan T, void* __restrict__ out_v) {
+    constexpr int CH = 16 / ES, EW = ES / 4, TA = 16 * CH, TB = 64, PA = TA / 32;
+    extern __shared__ __align__(16) uint32_t ring[];  // kTrStages x (TB x 64 words)
+    const char* __restrict__ src = (const char*)T.src;
+    char* __restrict__ out = (char*)out_v;
+    const int tid = threadIdx.x;
+    const int aq = tid & 15, br = tid >> 4;
+    const int lane = tid & 31, w = tid >> 5;
+    const int bq_lo = lane & 7, a_lo = lane >> 3;
+
+    auto locate = [&](uint64_t tile, int64_t& src_base, int64_t& out_base, uint64_t& a0, uint64_t& b0) {
+        const uint64_t tb = tile % T.tiles_b;
+        uint64_t r = tile / T.tiles_b;
+        const uint64_t ta = r % T.tiles_a;
+        uint64_t batch = r / T.tiles_a;
+        src_base = T.src_offset; out_base = 0;
+#pragma unroll
+        for (int k = kMaxRank - 1; k >= 0; --k) {
+            if (k < T.n_batch) {
+                const uint64_t c = batch % T.batch_len[k];
+                batch /= T.batch_len[k];
+                src_base += (int64_t)c * T.batch_src_stride[k];
+                out_base += (int64_t)c * T.batch_out_stride[k];
+            }
+        }
+        a0 = ta * TA; b0 = tb * TB;
+    };
+    auto issue = [&](uint64_t tile, int stage) {
+        int64_t src_base, out_base; uint64_t a0, b0;
+        locate(tile, src_base, out_base, a0, b0);
+        uint32_t* sm = ring + stage * (TB * 64);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int b_l = p * 16 + br;
+            const uint64_t b = b0 + b_l, a = a0 + (uint64_t)aq * CH;
+            const bool valid = b < T.len_b && a < T.len_a;
+            const int64_t e = valid ? src_base + (int64_t)b * T.src_stride_b + (int64_t)a : T.src_offset;
+            const int chunk = aq ^ ((b_l / CH) & 7);
+            cp_async16(sm + b_l * 64 + chunk * 4, src + e * ES, valid);
+        }
+    };
+
+    const uint64_t stride = gridDim.x;
+    uint64_t next = blockIdx.x;  // next tile to issue
+#pragma unroll
+    for (int s = 0; s < kTrStages - 1; ++s) {
+        if (next < T.n_tiles) issue(next, s);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        next += stride;
+    }
+    int it = 0;
+    for (uint64_t tile = blockIdx.x; tile < T.n_tiles; tile += stride, ++it) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kTrStages - 2) : "memory");
+        __syncthreads();  // tile `it` has landed for every thread, and stage (it-1) % kTrStages is drained
+        if (next < T.n_tiles) issue(next, (it + kTrStages - 1) % kTrStages);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        next += stride;
+
+        int64_t src_base, out_base; uint64_t a0, b0;
+        locate(tile, src_base, out_base, a0, b0);
+        const uint32_t* smem = ring + (it % kTrStages) * (TB * 64);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int a_l = 4 * (w + 8 * (p % PA)) + a_lo;
+            const int bq = bq_lo + 8 * (p / PA);
+            uint32_t wds[4];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int b_l = bq * CH + i;
+                const int word = b_l * 64 + (((a_l / CH) ^ (bq & 7)) * 4) + (a_l % CH) * EW;
+                if constexpr (ES == 4) wds[i] = smem[word];
+                else { const uint2 t = *reinterpret_cast<const uint2*>(&smem[word]); wds[2 * i] = t.x; wds[2 * i + 1] = t.y; }
+            }
+            const uint64_t a = a0 + a_l, b = b0 + (uint64_t)bq * CH;
+            const int64_t e = out_base + (int64_t)a * T.out_stride_a + (int64_t)b;
+            if (a < T.len_a && b < T.len_b)
+                asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(out + e * ES), "r"(wds[0]), "r"(wds[1]), "r"(wds[2]), "r"(wds[3]) : "memory");
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+static bool transpose_vec_ok(const TransposePlan& T, const void* out) {
     const int ch = 16 / T.esize;
     bool vec = ((uintptr_t)T.src + (uintptr_t)(T.src_offset * T.esize)) % 16 == 0 && ((uintptr_t)out % 16) == 0 && T.src_stride_b % ch == 0 &&
                T.out_stride_a % ch == 0 && T.len_a % ch == 0 && T.len_b % ch == 0;
     for (int k = 0; k < T.n_batch; ++k) vec = vec && T.batch_src_stride[k] % ch == 0 && T.batch_out_stride[k] % ch == 0;
+    return vec;
+}
+
+static bool use_pipe() {
+    static const bool on = [] { const char* e = getenv("MDIM_TR_PIPE"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+void launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t stream) {
+    const bool vec = transpose_vec_ok(T, out);
+    constexpr int smem = kTrStages * 64 * 64 * 4;
+    if (vec && use_pipe()) {
+        if (T.esize == 4) k_transpose_pipe<4><<<grid, kTrThreads, smem, stream>>>(T, out);
+        else k_transpose_pipe<8><<<grid, kTrThreads, smem, stream>>>(T, out);
+        return;
+    }
     if (T.esize == 4) {
         if (vec) k_transpose<4, true><<<grid, kTrThreads, 0, stream>>>(T, out);
         else k_transpose<4, false><<<grid, kTrThreads, 0, stream>>>(T, out);
@@ -135,7 +248,8 @@ void launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t 
 
 int transpose_max_ctas_per_sm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_transpose<4, true>, kTrThreads, 0);
+    if (use_pipe()) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_transpose_pipe<4>, kTrThreads, kTrStages * 64 * 64 * 4);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_transpose<4, true>, kTrThreads, 0);
     return n > 0 ? n : 1;
 }
 

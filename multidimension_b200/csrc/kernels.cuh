@@ -15,12 +15,12 @@ constexpr int kEvalThreads = 256;
 // All operands are read-only and never alias `out` (C-ABI contract), so loads use the
 // non-coherent path; stores are streaming (evict-first) because nothing re-reads the output.
 // ------------------------------------------------------------------------------------------------
-template <class Sig, class S, int V, int MAXD, bool WIDE, int MAXR>
+template <class Sig, class S, int V, int MAXD, bool WIDE, int MAXR, int VPT>
 __global__ void __launch_bounds__(kEvalThreads)
 k_eval(const __grid_constant__ Program P, void* __restrict__ out, ErrWord* __restrict__ err, uint64_t g_begin, uint64_t g_end) {
     const uint64_t step = (uint64_t)gridDim.x * kEvalThreads;
     for (uint64_t g = g_begin + (uint64_t)blockIdx.x * kEvalThreads + threadIdx.x; g < g_end; g += step)
-        eval_vector<Sig, S, V, MAXD, WIDE, MAXR>(P, out, err, g);
+        eval_vector<Sig, S, V, MAXD, WIDE, MAXR, VPT>(P, out, err, g);
 }
 
 using EvalKernel = void (*)(const Program, void*, ErrWord*, uint64_t, uint64_t);
@@ -28,6 +28,7 @@ using EvalKernel = void (*)(const Program, void*, ErrWord*, uint64_t, uint64_t);
 struct EvalVariant {
     const char* name;
     int slot_bytes, vec, max_depth, wide, maxr;  // maxr: iteration axes walked (1 = contiguous stream)
+    int vpt;                                     // vectors per thread trip
     const SigInstr* sig;  // nullptr = interpreter
     int sig_n;
     EvalKernel fn;

@@ -8,6 +8,7 @@
 // (tiled transpose, last-axis fold).  Host-only code; no CUDA calls.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -80,7 +81,11 @@ struct Builder {
     // per original node: canonical strides (LEAF/IOTA/GATHER)
     int64_t cstride[MDIM_MAX_NODES][kMaxRank];
     int depth = 0, max_depth = 0;
-    int force_vec = 0;  // 0 = widest that divides the innermost axis
+    int force_vec = 0;
+    bool no_vpt = false;
+    // canonical axis g (out axes outermost-first, then reduction axes) -> device program axis:
+    // the out axes are stored INNERMOST FIRST, so the vector axis is always program axis 0
+    int pa(int g) const { return g < rank ? rank - 1 - g : g; }  // 0 = widest that divides the innermost axis
 
     int validate();
     void canonical_axes();
@@ -258,8 +263,8 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
         memset(&A, 0, sizeof A);
         A.ptr = n.data;
         A.offset = n.offset;
-        for (int g = 0; g < kMaxRank; ++g) A.stride[g] = g < n_axes ? cstride[ni][g] : 0;
-        A.inner = rank > 0 ? A.stride[rank - 1] : 0;
+        for (int g = 0; g < n_axes; ++g) A.stride[pa(g)] = cstride[ni][g];
+        A.inner = rank > 0 ? A.stride[0] : 0;
         *slot = P.n_addr++;
         return MDIM_OK;
     };
@@ -269,19 +274,19 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
             int slot; int st = new_addr(&slot); if (st) return st;
             const Addr& A = P.addr[slot];
             const int es = dtype_size(n.dtype);
-            const int64_t s_in = rank > 0 ? A.stride[rank - 1] : 0;
+            const int64_t s_in = rank > 0 ? cstride[ni][rank - 1] : 0;
             int opc;
             if (rank == 0 || s_in == 0) opc = OPC_LEAF_BCAST;
             else if (s_in == 1) {
                 const int64_t align = std::min<int64_t>(16, (int64_t)V * es);
                 bool ok = (((uintptr_t)A.ptr + (uintptr_t)(A.offset * es)) % align) == 0;
                 for (int g = 0; g < n_axes && ok; ++g)
-                    if (g != rank - 1 && ((A.stride[g] * es) % align) != 0) ok = false;
+                    if (g != rank - 1 && ((cstride[ni][g] * es) % align) != 0) ok = false;
                 opc = ok ? OPC_LEAF_VEC : OPC_LEAF_STRIDED;
             } else opc = OPC_LEAF_STRIDED;
             in.opc = (uint8_t)opc; in.slot = (uint16_t)slot;
             if (opc == OPC_LEAF_VEC)  // re-read along a broadcast output axis => worth keeping in L1
-                for (int g = 0; g < rank; ++g) if (A.stride[g] == 0 && len[g] > 1) in.aux = 1;
+                for (int g = 0; g < rank; ++g) if (cstride[ni][g] == 0 && len[g] > 1) in.aux = 1;
             return push_instr(in);
         }
         case MDIM_NODE_IOTA: {
@@ -317,11 +322,11 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
                 memset(&pr, 0, sizeof pr);
                 const int a = axis_map[n.axis_a[p]];
                 const int b = n.axis_b[p] >= 0 ? axis_map[n.axis_b[p]] : -1;
-                pr.coef[a] += 1;
-                if (b >= 0) pr.coef[b] -= 1;
-                else if (n.axis_c[p] >= len[a]) { pr.coef[a] = 0; pr.rhs = 1; }  // never on the diagonal
+                pr.coef[pa(a)] += 1;
+                if (b >= 0) pr.coef[pa(b)] -= 1;
+                else if (n.axis_c[p] >= len[a]) { pr.coef[pa(a)] = 0; pr.rhs = 1; }  // never on the diagonal
                 else pr.rhs = (int64_t)n.axis_c[p];
-                pr.lane_coef = rank > 0 ? pr.coef[rank - 1] : 0;
+                pr.lane_coef = rank > 0 ? pr.coef[0] : 0;
                 P.pred[P.n_pred++] = pr; own_n++;
             }
             const bool lazy = has_err_source[child[ni][0]];
@@ -392,7 +397,7 @@ int Builder::emit() {
     const int root = e->n_nodes - 1;
     P.rank = rank; P.red_rank = red_rank;
     P.out_dtype = e->nodes[root].dtype;
-    for (int g = 0; g < n_axes; ++g) P.length[g] = len[g];
+    for (int g = 0; g < n_axes; ++g) P.length[pa(g)] = len[g];
     uint64_t out_elems = 1, red_count = 1;
     for (int g = 0; g < rank; ++g) out_elems *= len[g];
     for (int g = rank; g < n_axes; ++g) red_count *= len[g];
@@ -417,8 +422,17 @@ int Builder::emit() {
             if (len[rank - 1] % (uint64_t)cand[i] == 0) { V = cand[i]; break; }
     }
     if (force_vec) V = force_vec;
+    // Vectors per thread trip along the vector axis.  Measured on B200 (round 1): 4 consecutive vectors per
+    // thread halve the throughput of rank-N chains (lanes 128 B apart: every warp instruction touches 32
+    // separate lines), so coalescing wins over amortising the decode; the machinery stays for experiments.
+    int VPT = 1;
+    if (rank >= 2 && V > 1 && !force_vec && !no_vpt && !(flags & MDIM_COLLECT_NO_STATIC) && getenv("MDIM_VPT4")) {
+        const uint64_t inner_vecs = len[rank - 1] / (uint64_t)V;
+        if (inner_vecs % 4 == 0 && out_elems / ((uint64_t)V * 4) >= (1ull << 16)) VPT = 4;
+    }
+    plan->vpt = VPT; P.vpt = VPT;
     plan->vec = V; P.vec = V;
-    P.n_vec = out_elems / (uint64_t)V;
+    P.n_vec = out_elems / ((uint64_t)V * (uint64_t)VPT);  // work items: one per thread trip
 
     // 32-bit coordinate path needs: vectors < 2^31, every axis < 2^31, every stride in int32
     bool wide = P.n_vec >= (1ull << 31);
@@ -441,10 +455,11 @@ int Builder::emit() {
     plan->n_axes = n_axes;
     for (int g = 0; g < kMaxRank; ++g) {
         uint64_t L = 1;
-        if (g < rank) L = (g == rank - 1) ? len[g] / (uint64_t)V : len[g];
-        P.dec_len[g] = L;
-        P.dec_scale[g] = (g == rank - 1) ? (uint32_t)V : 1u;
-        find_divisor((uint32_t)std::min<uint64_t>(L, 0x7fffffffull), &P.div_mul[g], &P.div_shr[g]);
+        if (g < rank) L = (g == rank - 1) ? len[g] / ((uint64_t)V * (uint64_t)VPT) : len[g];
+        const int a = g < n_axes ? pa(g) : g;
+        P.dec_len[a] = L;
+        P.dec_scale[a] = (g == rank - 1) ? (uint32_t)(V * VPT) : 1u;
+        find_divisor((uint32_t)std::min<uint64_t>(L, 0x7fffffffull), &P.div_mul[a], &P.div_shr[a]);
     }
     depth = 0; max_depth = 0;
     int st = gen(root, 0, 0);
@@ -586,10 +601,18 @@ int plan_expr(const mdim_expr* e, uint32_t flags, Plan* plan, char* why_buf, siz
         if (st) { delete b; return st; }
     }
     plan->kind = (b->rank <= 1 && b->red_rank == 0) ? KK_STREAM : KK_GENERIC;
+    const int need_maxr = plan->kind == KK_STREAM ? 1 : std::max(1, plan->n_axes);
     if (!(flags & MDIM_COLLECT_NO_STATIC))
-        plan->static_id = find_static_signature(plan->sig, plan->sig_len, plan->slot_bytes, plan->vec);
-    snprintf(plan->describe, sizeof plan->describe, "%s.%s s%d v%d%s rank=%d+%d depth=%d instr=%d",
-             plan->kind == KK_STREAM ? "stream" : "generic", plan->static_id >= 0 ? "static" : "interp", plan->slot_bytes * 8, plan->vec,
+        plan->static_id = find_static_signature(plan->sig, plan->sig_len, plan->slot_bytes, plan->vec, plan->vpt, need_maxr, plan->wide);
+    if (plan->vpt > 1 && plan->static_id < 0) {  // several vectors per trip exist only as pre-instantiated signatures
+        b->no_vpt = true;
+        st = b->emit();
+        if (st) { delete b; return st; }
+        if (!(flags & MDIM_COLLECT_NO_STATIC))
+            plan->static_id = find_static_signature(plan->sig, plan->sig_len, plan->slot_bytes, plan->vec, plan->vpt, need_maxr, plan->wide);
+    }
+    snprintf(plan->describe, sizeof plan->describe, "%s.%s s%d v%dx%d%s rank=%d+%d depth=%d instr=%d",
+             plan->kind == KK_STREAM ? "stream" : "generic", plan->static_id >= 0 ? "static" : "interp", plan->slot_bytes * 8, plan->vec, plan->vpt,
              plan->wide ? " wide" : "", b->rank, b->red_rank, plan->max_depth, plan->prog.n_instr);
     if (!(flags & MDIM_COLLECT_NO_FASTPATH)) {
         st = b->detect_fast_paths();

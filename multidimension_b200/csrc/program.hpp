@@ -74,11 +74,15 @@ enum ProgFlags : uint32_t {
 };
 
 struct Program {
+    // Axis numbering of every per-axis array below: the output axes INNERMOST FIRST (axis 0 is the
+    // vector axis, axis rank-1 the outermost), then the reduction axes in iteration order.
     int32_t rank;      // coalesced output axes
     int32_t red_rank;  // coalesced reduction axes
     int32_t n_instr, n_addr, n_pred;
     int32_t out_dtype;
-    int32_t vec;  // lanes per thread along the innermost output axis
+    int32_t vec;  // lanes per vector along the innermost output axis (program axis 0)
+    int32_t vpt;  // consecutive vectors per thread trip along that axis
+    int32_t pad0;
     uint32_t flags;
     uint64_t length[kMaxRank];  // coalesced lengths: out axes then reduction axes (elements)
     uint64_t dec_len[kMaxRank];   // decode length of axis a: innermost out axis in vectors; 1 if not an out axis
@@ -148,6 +152,7 @@ struct Plan {
     int32_t kind;
     int32_t slot_bytes;  // 4 or 8: width of the value-stack slots
     int32_t vec;
+    int32_t vpt;         // vectors per thread trip
     int32_t wide;        // 64-bit coordinates/strides
     int32_t n_axes;      // rank + red_rank after canonicalisation (selects the MAXR instantiation)
     int32_t max_depth;
@@ -167,6 +172,6 @@ int dtype_size(int dt);
 const char* status_string(int st);
 
 // Signature registry (defined with the kernels; the planner only needs lookup by bytes).
-int find_static_signature(const char* sig, int sig_len, int slot_bytes, int vec);
+int find_static_signature(const char* sig, int sig_len, int slot_bytes, int vec, int vpt, int need_maxr, int wide);
 
 }  // namespace mdim

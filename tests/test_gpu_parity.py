@@ -241,7 +241,7 @@ def config5(P_, Q, R, rng):
     return z.map(lambda p: p[0] * p[1] + np.float32(1))
 
 
-@pytest.mark.parametrize("dims", [(4, 4, 8), (6, 5, 16), (3, 7, 5), (8, 8, 64)])
+@pytest.mark.parametrize("dims", [(4, 4, 8), (6, 5, 16), (3, 7, 5), (8, 8, 64), (16, 16, 64)])
 def test_rank5_chain(ctx, dims):
     v = config5(*dims, np.random.default_rng(sum(dims)))
     assert v.I == (((usize, usize), (usize, usize)), usize)
