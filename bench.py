@@ -337,6 +337,12 @@ def main():
     if not args.no_ops and world == 1:
         result["ops"] = bench_ops(ctx, torch, ta, tout, dev_array, out_storage, time_launches, peak, args)
 
+    # ---- the ops with a real exchange step, N > 1 ----------------------------------------------------------------------------------
+    if not args.no_ops and world > 1:
+        multi = bench_multi_ops(ctx, torch, dist, rank, world, ta, tout, dev_array, out_storage, time_launches, barrier)
+        if rank == 0:
+            result["ops_multi"] = multi
+
     # ---- CPU restatement beside it (rank 0, N=1) -----------------------------------------------------------------------------------
     if not args.no_cpu and world == 1 and rank == 0:
         pin_to_one_core()
@@ -449,6 +455,76 @@ def bench_ops(ctx, torch, ta, tout, dev_array, out_storage, time_launches, peak,
     ms, _ = time_launches(lambda: v5.collect(out=o5, flags=F.COLLECT_ASYNC), steps, 3)
     line("c5_rank5_transpose_diagonal_broadcast_map", 4 * (1 << 30) + 4 * Pn * Qn + 4 * Rn, ms, v5.describe())
     return ops
+
+
+def bench_multi_ops(ctx, torch, dist, rank, world, ta, tout, dev_array, out_storage, time_launches, barrier):
+    """N > 1 only (SURVEY.md §8e rows with a collective): compose() onto a SHARDED source — peer-mapped
+    reads over NVLink vs NCCL all-gather + local gather — and a fold over the sharded axis + all-reduce.
+    Aggregate GB/s on algorithmic bytes, device time, max over ranks."""
+    import multidimension_b200 as P
+    from multidimension_b200 import usize, Array, Add, fold_rows, _ffi as F
+    from multidimension_b200.runtime import Storage
+    from multidimension_b200 import sharding
+    out = {}
+    n_src = 1 << 30
+    n_idx = (1 << 28) // world          # this rank's block of the index Array
+    block = n_src // world              # this rank's block of the source
+    src_block = ta[:block]
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0x5EED0003 + rank)
+    tidx = torch.randint(0, n_src, (n_idx,), device="cuda", dtype=torch.int64, generator=g)
+    idx = dev_array(usize, n_idx, tidx, usize)
+    o = out_storage(tout[:n_idx], F.F32)
+    # (a) peer-mapped source: every rank's block is IPC-mapped into every other rank
+    local = Storage.wrap_device(ctx, F.F32, block, src_block.data_ptr(), keep=src_block)
+    peers = sharding.peer_source(local, n_src, ctx=ctx)
+    v = idx.compose(Array(usize, n_src, peers, "f32"))
+    v.collect(out=o)
+    full = [torch.empty_like(src_block) for _ in range(world)]
+    dist.all_gather(full, src_block)
+    full = torch.cat(full)
+    assert torch.equal(tout[:n_idx], full[tidx]), "peer-sharded gather mismatch"
+    ms, _ = time_launches(lambda: v.collect(out=o, flags=F.COLLECT_ASYNC), 5, 3)
+    alg = 16 * n_idx * world
+    out["compose_sharded_source_peer_mapped"] = {"GB/s": round(alg / (ms * 1e-3) / 1e9, 1), "ms": round(ms, 4), "kernel": v.describe(),
+                                                 "note": "gather kernel reads the owning peer's HBM over NVLink; no collective"}
+    # (b) NCCL all-gather of the source, then a local gather (what the north star names)
+    full_buf = torch.empty(n_src, device="cuda", dtype=torch.float32)
+    v2 = idx.compose(dev_array(usize, n_src, full_buf, "f32"))
+
+    def ag_then_gather():
+        dist.all_gather_into_tensor(full_buf, src_block)
+        v2.collect(out=o, flags=F.COLLECT_ASYNC)
+    ag_then_gather()
+    torch.cuda.synchronize()
+    assert torch.equal(tout[:n_idx], full[tidx]), "all-gather + gather mismatch"
+    ms, _ = time_launches(ag_then_gather, 5, 3)
+    out["compose_sharded_source_allgather"] = {"GB/s": round(alg / (ms * 1e-3) / 1e9, 1), "ms": round(ms, 4),
+                                               "note": "ncclAllGather of the 4 GiB source + local gather"}
+    peers.close()
+    del full, full_buf, tidx
+    # (c) fold over the SHARDED (outermost) axis + all-reduce: a (1024,1024,256) f32 Array sharded on axis 0
+    I, J, K = 1024 // world, 1024, 256
+    t4 = ta[: I * J * K]
+    a4 = dev_array((usize, usize, usize), (I, J, K), t4, "f32")
+    part_view = fold_rows(a4.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize)), (usize, usize), usize, Add, np.float32(0))
+    tpart = torch.empty(J * K, device="cuda", dtype=torch.float32)
+    opart = out_storage(tpart, F.F32)
+
+    def fold_allreduce():
+        part_view.collect(out=opart, flags=F.COLLECT_ASYNC)
+        dist.all_reduce(tpart)
+    fold_allreduce()
+    torch.cuda.synchronize()
+    ref = t4.view(I, J * K).double().sum(dim=0)
+    dist.all_reduce(ref)
+    rel = ((tpart.double() - ref).abs() / ref.abs()).max().item()
+    assert rel < 1e-5, f"sharded-axis fold error {rel}"
+    ms, _ = time_launches(fold_allreduce, 5, 3)
+    alg = (4 * I * J * K) * world + 4 * J * K
+    out["fold_sharded_axis_allreduce"] = {"GB/s": round(alg / (ms * 1e-3) / 1e9, 1), "ms": round(ms, 4), "kernel": part_view.describe(),
+                                          "max_rel_err_vs_f64": rel, "note": "per-rank partial fold + ncclAllReduce(sum) of 1 MiB"}
+    return out
 
 
 if __name__ == "__main__":

@@ -10,10 +10,11 @@ from .lowering import Unsupported
 from .ops import Pair, Add, Sub, Mul, Div, Rem, BitAnd, BitOr, BitXor, Shl, Shr, Neg, Not, Abs, Sqrt, Cast, Fold
 from .runtime import Context, Storage, default_context, set_default_context
 from .view import View, Array, All, all_, Scalar, fold_rows
+from . import sharding
 
 __all__ = [
     "MdimError", "Panic", "Unsupported", "LIB_PATH", "usize", "Reversed", "Fixed", "Coated",
     "Pair", "Add", "Sub", "Mul", "Div", "Rem", "BitAnd", "BitOr", "BitXor", "Shl", "Shr",
     "Neg", "Not", "Abs", "Sqrt", "Cast", "Fold", "Context", "Storage", "default_context", "set_default_context",
-    "View", "Array", "All", "all_", "Scalar", "fold_rows",
+    "View", "Array", "All", "all_", "Scalar", "fold_rows", "sharding",
 ]

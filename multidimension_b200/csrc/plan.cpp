@@ -511,6 +511,7 @@ int Builder::detect_fast_paths() {
             T.tiles_a = (T.len_a + tile_a - 1) / tile_a; T.tiles_b = (T.len_b + 63) / 64;
             uint64_t nb = 1; for (int b = 0; b < T.n_batch; ++b) nb *= T.batch_len[b];
             T.n_tiles = T.tiles_a * T.tiles_b * nb;
+            { const char* ord = getenv("MDIM_TR_ORDER"); T.a_fastest = ord ? atoi(ord) : 0; }
             plan->kind = KK_TRANSPOSE;
             snprintf(plan->describe, sizeof plan->describe, "transpose.tile64 es%d a=%llu b=%llu batch=%llu", es,
                      (unsigned long long)T.len_a, (unsigned long long)T.len_b, (unsigned long long)nb);

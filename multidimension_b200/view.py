@@ -438,7 +438,8 @@ class Array(View):
         stride = {a: s for a, s in stride.items()}
 
         def leaf(s):
-            return L.Node(F.LEAF, s.dtype, buf=s, stride=dict(stride))
+            peers = getattr(s, "peers", None)
+            return L.Node(F.LEAF, s.dtype, buf=s, stride=dict(stride), peers=peers, peer_block=getattr(s, "block", 0))
         value = L.map_value(self.storage, leaf) if isinstance(self.storage, tuple) else leaf(self.storage)
         return groups, value
 

@@ -1,0 +1,135 @@
+"""Multi-GPU partitioning: host-side logic on CPU with world_size-2 gloo, the
+peer-mapped gather kernel path on one GPU (two "peers" that are buffers of the same device)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import oracle_collect, emu_collect, assert_same_bits
+import multidimension_b200 as P
+from multidimension_b200 import usize, Array, Scalar, Add, fold_rows, _ffi as F
+from multidimension_b200.runtime import Storage
+from multidimension_b200.sharding import shard_bounds, equal_block, PeerStorage
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 64, 1000):
+        for w in (1, 2, 3, 8):
+            blocks = [shard_bounds(n, w, r) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+            assert equal_block(n, w) * w >= n
+
+
+def _peer_case(rng, n_src, n_idx, world):
+    src = rng.uniform(-1, 1, n_src).astype(np.float32)
+    block = equal_block(n_src, world)
+    padded = np.zeros(block * world, np.float32)
+    padded[:n_src] = src
+    shards = [np.ascontiguousarray(padded[p * block:(p + 1) * block]) for p in range(world)]
+    idx = rng.integers(0, n_src, n_idx).astype(np.uint64)
+    return src, shards, block, idx
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_peer_sharded_compose_matches_replicated(world):
+    rng = np.random.default_rng(world)
+    src, shards, block, idx = _peer_case(rng, 1000, 5000, world)
+    peers = PeerStorage(F.F32, src.size, [s.ctypes.data for s in shards], block, keep=shards)
+    sharded = Array.new(usize, idx.size, idx).compose(Array(usize, src.size, peers, "f32"))
+    replicated = Array.new(usize, idx.size, idx).compose(Array.new(usize, src.size, src))
+    want = oracle_collect(replicated)
+    assert_same_bits(oracle_collect(sharded), want)
+    assert_same_bits(emu_collect(sharded), want)
+    with pytest.raises(P.Unsupported):  # a sharded Array is only readable through a gather
+        oracle_collect(Array(usize, src.size, peers, "f32") * Scalar(2.0, "f32"))
+
+
+@pytest.mark.gpu
+def test_peer_sharded_compose_gpu():
+    ctx = P.Context(0)
+    rng = np.random.default_rng(5)
+    src, shards, block, idx = _peer_case(rng, 100000, 1 << 18, 2)
+    dev = [Storage.from_host(F.F32, s).ensure_device(ctx) for s in shards]
+    peers = PeerStorage(F.F32, src.size, [d.dptr for d in dev], block, keep=dev, ctx=ctx)
+    sharded = Array.new(usize, idx.size, idx).compose(Array(usize, src.size, peers, "f32"))
+    got = sharded.collect(location="device", ctx=ctx).as_ref()
+    assert_same_bits(got, src[idx.astype(np.int64)])
+    bad = idx.copy()
+    bad[777] = src.size
+    with pytest.raises(P.Panic, match=f"Index {src.size} is out of bounds for size {src.size}"):
+        Array.new(usize, bad.size, bad).compose(Array(usize, src.size, peers, "f32")).collect(location="device", ctx=ctx)
+    ctx.close()
+
+
+# ---- world_size-2 gloo: the per-rank flow of bench.py / a sharded application ---------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    from multidimension_b200.sharding import all_reduce_partial
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(99)  # same data on every rank; each takes its block
+    I, J, K = 6, 5, 32
+    a = rng.uniform(0, 1, I * J * K).astype(np.float32)
+    b = rng.uniform(-1, 1, I * J * K).astype(np.float32)
+    lo, hi = shard_bounds(I, world, rank)
+    blk = slice(lo * J * K, hi * J * K)
+    A = Array.new((usize, usize, usize), (hi - lo, J, K), a[blk])
+    B = Array.new((usize, usize, usize), (hi - lo, J, K), b[blk])
+    # (1) elementwise: independent shards, no collective
+    ew = emu_collect(A.zip(B).map(lambda p: p[0] * p[1] + np.float32(1)))
+    # (2) fold over a NON-sharded axis + broadcast subtract: independent shards
+    mean = fold_rows(A, (usize, usize), usize, Add, np.float32(0)) / Scalar(float(K), "f32")
+    c4 = emu_collect(A - mean.iso((usize, usize, ())))
+    # (3) fold over the SHARDED axis: per-rank partial of the output shape, then all-reduce
+    At = A.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize))  # (J,K) x local I
+    part = emu_collect(fold_rows(At, (usize, usize), usize, Add, np.float32(0)))
+    st = Storage.from_host(F.F32, part.copy())
+    all_reduce_partial(st, "sum")
+    # (4) compose with a sharded source: all-gather the source, gather locally (index shard per rank)
+    src_block = torch.from_numpy(a[rank * (a.size // world):(rank + 1) * (a.size // world)].copy())
+    gathered = [torch.empty_like(src_block) for _ in range(world)]
+    dist.all_gather(gathered, src_block)
+    full_src = torch.cat(gathered).numpy()
+    idx = rng.integers(0, a.size, 4000).astype(np.uint64)
+    ilo, ihi = shard_bounds(idx.size, world, rank)
+    comp = emu_collect(Array.new(usize, ihi - ilo, idx[ilo:ihi]).compose(Array.new(usize, full_src.size, full_src)))
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ew=ew, c4=c4, red=st.host, comp=comp)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_sharded_flows(tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
+    rng = np.random.default_rng(99)
+    I, J, K = 6, 5, 32
+    a = rng.uniform(0, 1, I * J * K).astype(np.float32)
+    b = rng.uniform(-1, 1, I * J * K).astype(np.float32)
+    A = Array.new((usize, usize, usize), (I, J, K), a)
+    B = Array.new((usize, usize, usize), (I, J, K), b)
+    assert_same_bits(np.concatenate([p["ew"] for p in parts]), oracle_collect(A.zip(B).map(lambda p: p[0] * p[1] + np.float32(1))))
+    mean = fold_rows(A, (usize, usize), usize, Add, np.float32(0)) / Scalar(float(K), "f32")
+    assert_same_bits(np.concatenate([p["c4"] for p in parts]), oracle_collect(A - mean.iso((usize, usize, ()))))
+    # sharded-axis fold: order differs from the sequential reference -> 1e-6 relative (north star)
+    At = A.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize))
+    want = oracle_collect(fold_rows(At, (usize, usize), usize, Add, np.float32(0)))
+    for p in parts:
+        assert np.max(np.abs(p["red"] - want) / np.abs(want)) <= 1e-6
+    idx = rng.integers(0, a.size, 4000).astype(np.uint64)
+    assert_same_bits(np.concatenate([p["comp"] for p in parts]), a[idx.astype(np.int64)])
