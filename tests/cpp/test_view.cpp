@@ -1,0 +1,150 @@
+// test_view.cpp — the reference's doctests and the BASELINE configs in miniature, written against the
+// C++ host mirror (include/mdim/view.hpp) so that they read like the reference's own tests.
+//   ./test_view oracle <liboracle.so>   CPU: the descriptor is executed by the C oracle (checker)
+//   ./test_view gpu <libmdim_b200.so>   B200: mdim_collect_host (sm_100a kernels through the C ABI)
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "../../include/mdim/view.hpp"
+
+using namespace mdim;
+using U2 = std::tuple<usize, usize>;
+using U3 = std::tuple<usize, usize, usize>;
+
+static int failures = 0, checks = 0;
+#define CHECK(cond) do { ++checks; if (!(cond)) { ++failures; std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); } } while (0)
+template <class V> struct same { using type = V; };
+template <class V> static bool eq(const std::vector<V>& a, const std::vector<typename same<V>::type>& b) { return a == b; }
+
+static void* sym(void* lib, const char* name) {
+    void* p = dlsym(lib, name);
+    if (!p) { std::printf("missing symbol %s\n", name); std::exit(2); }
+    return p;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 3) { std::printf("usage: test_view oracle|gpu <library>\n"); return 2; }
+    void* lib = dlopen(argv[2], RTLD_NOW);
+    if (!lib) { std::printf("dlopen: %s\n", dlerror()); return 2; }
+    Executor ex;
+    mdim_ctx* ctx = nullptr;
+    if (std::string(argv[1]) == "oracle") {
+        auto f = (int (*)(const mdim_expr*, void*, mdim_error_info*))sym(lib, "mdim_oracle_collect");
+        ex = Executor{[f](const mdim_expr* e, void* out, mdim_error_info* err) { return f(e, out, err); }};
+    } else {
+        auto init = (int (*)(int, mdim_ctx**))sym(lib, "mdim_init");
+        if (init(0, &ctx) != MDIM_OK) { std::printf("mdim_init failed (no sm_100 device?)\n"); return 2; }
+        ex = Executor::device(ctx, (int (*)(mdim_ctx*, const mdim_expr*, void*, uint32_t))sym(lib, "mdim_collect_host"),
+                              (int (*)(mdim_ctx*, mdim_error_info*))sym(lib, "mdim_last_error"));
+    }
+
+    {   // src/view.rs:138-142: usize::all(5).collect() == [0,1,2,3,4]
+        CHECK(eq(all(5).collect(ex).as_ref(), {0ull, 1ull, 2ull, 3ull, 4ull}));
+    }
+    {   // src/view.rs:276-284: usize::all(3).map(|x| x + 10).diagonal(0)
+        auto a = (all(3) + Scalar<usize>(10)).diagonal(0).collect(ex);
+        CHECK(eq(a.as_ref(), {10ull, 0ull, 0ull, 0ull, 11ull, 0ull, 0ull, 0ull, 12ull}));
+        CHECK(a.size() == std::make_tuple(uint64_t(3), uint64_t(3)));
+    }
+    {   // src/view.rs:294-298: squares
+        CHECK(eq((all(5) * all(5)).collect(ex).as_ref(), {0ull, 1ull, 4ull, 9ull, 16ull}));
+    }
+    {   // src/view.rs:307-313: compose — Array<bool, usize> [2, 1] selecting from 3 items ("apple","body","crane" -> 0,1,2)
+        Array<bool, usize> a(Unit{}, {2, 1});
+        Array<usize, usize> b(3, {0, 1, 2});
+        auto ab = a.compose(b).collect(ex);
+        CHECK(eq(ab.as_ref(), {2ull, 1ull}));
+        Array<bool, usize> bad(Unit{}, {2, 3});
+        try { bad.compose(b).collect(ex); CHECK(false); }
+        catch (const Panic& p) { CHECK(std::string(p.what()) == "Index 3 is out of bounds for size 3"); CHECK(p.status == MDIM_ERR_OOB); }  // src/int.rs:17
+    }
+    {   // src/view.rs:499-506: binary::<_, Add>
+        Array<usize, usize> a(3, {9, 8, 7}), b(3, {10, 20, 30});
+        CHECK(eq(a.binary<Add>(b).collect(ex).as_ref(), {19ull, 28ull, 37ull}));
+        CHECK(eq((a + b).collect(ex).as_ref(), {19ull, 28ull, 37ull}));
+        Array<usize, usize> c(4, {1, 2, 3, 4});
+        try { (a + c); CHECK(false); } catch (const Panic& p) { CHECK(std::string(p.what()) == "Unequal sizes"); }  // src/broadcast.rs:38
+    }
+    {   // src/view.rs:572-585: transpose of a 3x2
+        Array<U2, usize> a(std::make_tuple(uint64_t(3), uint64_t(2)), {0, 1, 10, 11, 20, 21});
+        auto t = a.transpose<Unit, usize, usize, Unit>();
+        CHECK(eq(t.collect(ex).as_ref(), {0ull, 10ull, 20ull, 1ull, 11ull, 21ull}));
+        // src/view.rs:596-608, 626-638: row / column
+        CHECK(eq(a.row<usize, usize>(1).collect(ex).as_ref(), {10ull, 11ull}));
+        CHECK(eq(a.column<usize, usize>(1).collect(ex).as_ref(), {1ull, 11ull, 21ull}));
+        CHECK(a.at(std::make_tuple(uint64_t(2), uint64_t(1))) == 21);  // src/array.rs:18-27
+        try { a.at(std::make_tuple(uint64_t(3), uint64_t(0))); CHECK(false); } catch (const Panic&) { CHECK(true); }
+        try { Array<U2, usize>(std::make_tuple(uint64_t(3), uint64_t(2)), {1, 2, 3}); CHECK(false); } catch (const Panic& p) { CHECK(p.status == MDIM_ERR_SIZE); }  // src/array.rs:12
+    }
+    {   // src/view.rs:477-487 shape: (usize, ()) zipped with ((), bool) broadcasts to (usize, bool)
+        Array<std::tuple<usize, Unit>, float> col(std::make_tuple(uint64_t(3), Unit{}), {1.f, 2.f, 3.f});
+        Array<std::tuple<Unit, bool>, float> rowv(std::make_tuple(Unit{}, Unit{}), {10.f, 20.f});
+        auto z = (col * rowv).collect(ex);
+        CHECK(eq(z.as_ref(), {10.f, 20.f, 20.f, 40.f, 30.f, 60.f}));
+    }
+    // ---- the BASELINE configs in miniature --------------------------------------------------------------
+    {   // config 2: a.zip(b).map(|(x,y)| x*y+1)  ==  a * b + Scalar(1.0)
+        const uint64_t n = 1000;
+        std::vector<float> av(n), bv(n);
+        for (uint64_t i = 0; i < n; ++i) { av[i] = std::sin((float)i); bv[i] = std::cos((float)i * 0.7f); }
+        Array<usize, float> a(n, av), b(n, bv);
+        auto c = (a * b + Scalar<float>(1.0f)).collect(ex);
+        bool same = true;
+        for (uint64_t i = 0; i < n; ++i) { volatile float m = av[i] * bv[i]; float want = m + 1.0f; same = same && std::memcmp(&want, &c.as_ref()[i], 4) == 0; }
+        CHECK(same);
+    }
+    {   // config 3: idx.compose(src)
+        const uint64_t n = 500, m = 77;
+        std::vector<uint64_t> iv(n); std::vector<float> sv(m);
+        for (uint64_t i = 0; i < n; ++i) iv[i] = (i * 2654435761ull) % m;
+        for (uint64_t i = 0; i < m; ++i) sv[i] = (float)i * 0.5f;
+        auto out = Array<usize, usize>(n, iv).compose(Array<usize, float>(m, sv)).collect(ex);
+        bool same = true; for (uint64_t i = 0; i < n; ++i) same = same && out.as_ref()[i] == sv[iv[i]];
+        CHECK(same);
+    }
+    {   // config 4: sum over the last index in SEQUENTIAL order, subtract the mean
+        const uint64_t I = 4, J = 5, K = 64;
+        std::vector<float> av(I * J * K);
+        for (size_t i = 0; i < av.size(); ++i) av[i] = (float)((i * 37) % 101) / 101.0f;
+        Array<U3, float> a(std::make_tuple(I, J, K), av);
+        auto sums = a.rows<U2, usize>().fold<Add>(0.0f);
+        auto mean = sums / Scalar<float>((float)K);
+        auto out = (a - mean.iso<std::tuple<usize, usize, Unit>>()).collect(ex);
+        bool same = true;
+        for (uint64_t r = 0; r < I * J; ++r) {
+            float s = 0.0f; for (uint64_t k = 0; k < K; ++k) s += av[r * K + k];
+            const float m = s / (float)K;
+            for (uint64_t k = 0; k < K; ++k) { float want = av[r * K + k] - m; same = same && std::memcmp(&want, &out.as_ref()[r * K + k], 4) == 0; }
+        }
+        CHECK(same);
+    }
+    {   // config 5: transpose -> diagonal -> broadcast -> x*y+1
+        const uint64_t P = 3, Q = 4, R = 8;
+        std::vector<float> av(P * Q), wv(R);
+        for (size_t i = 0; i < av.size(); ++i) av[i] = 1.0f + (float)i;
+        for (size_t i = 0; i < wv.size(); ++i) wv[i] = 0.25f * (float)(i + 1);
+        Array<U2, float> a(std::make_tuple(P, Q), av);
+        Array<usize, float> w(R, wv);
+        auto t = a.transpose<Unit, usize, usize, Unit>();                       // (((),(q,p)),()) in position space: (q, p)
+        auto d = t.iso<U2>().diagonal(0.0f);                                    // ((q,p),(q',p'))
+        auto d5 = d.iso<std::tuple<std::tuple<U2, U2>, Unit>>();
+        auto z = d5 * w.iso<std::tuple<Unit, usize>>() + Scalar<float>(1.0f);   // (((q,p),(q',p')), r)
+        auto out = z.collect(ex);
+        bool same = out.as_ref().size() == Q * P * Q * P * R;
+        size_t k = 0;
+        for (uint64_t q = 0; q < Q; ++q) for (uint64_t p = 0; p < P; ++p) for (uint64_t q2 = 0; q2 < Q; ++q2) for (uint64_t p2 = 0; p2 < P; ++p2)
+            for (uint64_t r = 0; r < R; ++r, ++k) {
+                const float x = (q == q2 && p == p2) ? av[p * Q + q] : 0.0f;
+                volatile float m = x * wv[r]; const float want = m + 1.0f;
+                same = same && std::memcmp(&want, &out.as_ref()[k], 4) == 0;
+            }
+        CHECK(same);
+    }
+    std::printf("%s: %d checks, %d failures\n", argv[1], checks, failures);
+    if (ctx) ((int (*)(mdim_ctx*))sym(lib, "mdim_shutdown"))(ctx);
+    return failures ? 1 : 0;
+}

@@ -1,0 +1,67 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/mdim.h declares, agrees with
+the ctypes mirror on struct layout, refuses to compute without a device, and plans the BASELINE chains
+onto the intended kernels (planning needs no GPU)."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, oracle_lib
+import multidimension_b200 as P
+from multidimension_b200 import _ffi as F, usize, Array, Scalar, Add, fold_rows
+
+
+def test_every_declared_symbol_is_exported():
+    lib = F.lib()
+    header = open(f"{ROOT}/include/mdim.h").read()
+    declared = set(re.findall(r"\b(mdim_[a-z_]+)\s*\(", header))
+    declared -= {"mdim_node", "mdim_expr"}
+    assert declared == {name for name, _r, _a in F.SYMBOLS}, declared ^ {n for n, _r, _a in F.SYMBOLS}
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.mdim_abi_version() == F.ABI_VERSION
+
+
+def test_struct_layout_matches_the_c_compiler():
+    o = oracle_lib()
+    assert C.sizeof(F.Node) == o.mdim_oracle_sizeof_node()
+    assert C.sizeof(F.Expr) == o.mdim_oracle_sizeof_expr()
+
+
+def test_no_cpu_fallback():
+    """Without an sm_100 device the context cannot be created; nothing computes on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(P.MdimError) as e:
+        P.Context(0)
+    assert e.value.status == F.ERR_CUDA
+    a = Array.new(usize, 4, np.arange(4, dtype=np.float32))
+    with pytest.raises(P.MdimError):
+        (a * a).collect()
+
+
+def test_planner_picks_the_intended_kernels():
+    rng = np.random.default_rng(0)
+    f = lambda *shape: rng.uniform(-1, 1, int(np.prod(shape))).astype(np.float32)
+    a, b = Array.new(usize, 1 << 12, f(1 << 12)), Array.new(usize, 1 << 12, f(1 << 12))
+    assert "SigMulAddCF32 r1" in a.zip(b).map(lambda p: p[0] * p[1] + np.float32(1)).describe()
+    assert "SigMulAddCF32 r1" in (a * b + Scalar(1.0, "f32")).describe()
+    m = Array.new((usize, usize), (128, 256), f(128, 256))
+    assert m.transpose((), usize, usize, ()).describe().startswith("transpose.tile64")
+    idx = Array.new(usize, 64, rng.integers(0, 1 << 12, 64).astype(np.uint64))
+    assert "SigGatherF32" in idx.compose(a).describe()
+    c = Array.new((usize, usize, usize), (4, 8, 64), f(4, 8, 64))
+    s = fold_rows(c, (usize, usize), usize, Add, np.float32(0))
+    assert s.describe().startswith("fold_rows ")
+    assert (c - (s / Scalar(64.0, "f32")).iso((usize, usize, ()))).describe().startswith("fold_rows.fused")
+    means = Array.new((usize, usize), (4, 8), f(4, 8))
+    assert "SigSubBcastF32" in (c - means.iso((usize, usize, ()))).describe()
+    w = Array.new(usize, 64, f(64))
+    q = Array.new((usize, usize), (4, 4), f(4, 4))
+    v5 = (q.transpose((), usize, usize, ()).diagonal(np.float32(0)).iso((((usize, usize), (usize, usize)), ()))
+          .zip(w.iso(((), usize))).map(lambda p: p[0] * p[1] + np.float32(1)))
+    assert "SigDiagMulAddCF32 r5" in v5.describe()
+    # contiguous arrays of any rank and any Iso regrouping collapse to the rank-1 stream kernel
+    assert "rank=1+0" in (c * c).describe() and "rank=1+0" in (c.iso(((usize, usize), usize)) * c.iso(((usize, usize), usize))).describe()
