@@ -25,10 +25,11 @@ static std::vector<EvalVariant>& registry() {
     static std::vector<EvalVariant> all = [] {
         std::vector<EvalVariant> v;
         int n = 0;
-        const EvalVariant* a = eval_variants_s32(&n);
-        v.insert(v.end(), a, a + n);
-        a = eval_variants_s64(&n);
-        v.insert(v.end(), a, a + n);
+        const EvalVariant* (*parts[])(int*) = {eval_variants_s32_static, eval_variants_s64_static, eval_variants_s32_interp, eval_variants_s64_interp};
+        for (auto part : parts) {
+            const EvalVariant* a = part(&n);
+            v.insert(v.end(), a, a + n);
+        }
         return v;
     }();
     return all;

@@ -1,4 +1,4 @@
-// k_eval_s64.cu — instantiations of the fused evaluator with 64-bit value slots (sm_100a).
+// k_eval_s32_static.cu — instantiations of the fused evaluator with 32-bit value slots (sm_100a).
 #include "kernels.cuh"
 #include "sigs.hpp"
 
@@ -10,12 +10,12 @@ static const EvalVariant kVariants[] = {
 #define X4(Sig, S, V, MAXD, WIDE, MAXR, VPT) \
     {#Sig, (int)sizeof(S), V, MAXD, WIDE ? 1 : 0, MAXR, VPT, sig_code<Sig>(), Sig::n, &k_eval<Sig, S, V, MAXD, WIDE, MAXR, VPT>},
 #define X(Sig, S, V, MAXD, WIDE, MAXR) X4(Sig, S, V, MAXD, WIDE, MAXR, 1)
-#include "variants_s64.inc"
+#include "variants_s32_static.inc"
 #undef X
 #undef X4
 };
 
-const EvalVariant* eval_variants_s64(int* n) {
+const EvalVariant* eval_variants_s32_static(int* n) {
     *n = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
     return kVariants;
 }

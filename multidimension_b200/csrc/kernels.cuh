@@ -34,9 +34,11 @@ struct EvalVariant {
     EvalKernel fn;
 };
 
-// defined in k_eval_s32.cu / k_eval_s64.cu
-const EvalVariant* eval_variants_s32(int* n);
-const EvalVariant* eval_variants_s64(int* n);
+// defined in k_eval_{s32,s64}_{interp,static}.cu (four translation units: the build parallelises over them)
+const EvalVariant* eval_variants_s32_interp(int* n);
+const EvalVariant* eval_variants_s32_static(int* n);
+const EvalVariant* eval_variants_s64_interp(int* n);
+const EvalVariant* eval_variants_s64_static(int* n);
 
 // ------------------------------------------------------------------------------------------------
 // K2: tiled transpose of one leaf (see k_transpose.cu)
