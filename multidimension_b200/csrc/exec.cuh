@@ -21,9 +21,11 @@
 
 #if defined(__CUDACC__)
 #define MDIM_FN __device__ __forceinline__
+#define MDIM_CE __host__ __device__ constexpr
 #else
 #include <math.h>
 #define MDIM_FN static inline __attribute__((always_inline))
+#define MDIM_CE constexpr
 #endif
 
 namespace mdim {
@@ -385,6 +387,7 @@ template <> struct CoordTraits<true> { using coord_t = uint64_t; using off_t = i
 
 template <bool WIDE, int MAXR> struct ThreadState {
     typename CoordTraits<WIDE>::coord_t c[MAXR];  // element coordinates of lane 0
+    typename CoordTraits<WIDE>::coord_t rk;       // coordinate along the fastest reduction axis
     uint64_t pos0;                                // linear output position of lane 0
     uint64_t red_k;                               // reduction step counter
     uint32_t mask;                                // lane-active mask (Diagonal laziness)
@@ -395,7 +398,7 @@ template <bool WIDE, int MAXR> struct ThreadState {
 template <bool WIDE, int MAXR>
 MDIM_FN typename CoordTraits<WIDE>::off_t addr_offset(const Program& P, int slot, const ThreadState<WIDE, MAXR>& ts) {
     using off_t = typename CoordTraits<WIDE>::off_t;
-    off_t off = (off_t)P.addr[slot].offset;
+    off_t off = (off_t)P.addr[slot].offset + (off_t)ts.rk * (off_t)P.addr[slot].rstride;
 #pragma unroll
     for (int a = 0; a < MAXR; ++a) off += (off_t)ts.c[a] * (off_t)P.addr[slot].stride[a];
     return off;
@@ -479,6 +482,23 @@ MDIM_FN void exec_gather(const Program& P, ErrWord* err, const Instr& I, S (&st)
             st[D - NC][l] = v;
         }
     }
+}
+
+// One step of Index::each over the reduction axes, last axis fastest (src/index.rs:122-124): the fastest
+// axis is the counter rk; only when it wraps do the slower axes (kept in c[]) move.
+template <bool WIDE, int MAXR> MDIM_FN void carry_red(const Program& P, ThreadState<WIDE, MAXR>& ts) {
+    bool carry = true;
+#pragma unroll
+    for (int a = MAXR - 1; a >= 0; --a) {
+        if (carry && a >= P.rank && a < P.rank + P.red_rank) {
+            ts.c[a] += 1;
+            if ((uint64_t)ts.c[a] >= P.length[a]) ts.c[a] = 0; else carry = false;
+        }
+    }
+}
+template <bool WIDE, int MAXR> MDIM_FN void advance_red(const Program& P, ThreadState<WIDE, MAXR>& ts) {
+    ts.rk += 1;
+    if ((uint64_t)ts.rk >= P.red_fast_len) { ts.rk = 0; carry_red<WIDE, MAXR>(P, ts); }
 }
 
 // Execute instruction I at compile-time stack depth D.  Returns the next pc.
@@ -566,6 +586,7 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
                 for (int a = 0; a < MAXR; ++a)
                     if (a >= P.rank) ts.c[a] = 0;
                 ts.red_k = 0;
+                ts.rk = 0;
                 if (P.red_count == 0) next = I.slot;  // empty row: skip the body and its FOLD_STEP
             }
             break;
@@ -577,14 +598,7 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
                     st[D - 2][l] = bin_op<S>(dtype, op, aux, st[D - 2][l], st[D - 1][l], arith);
                     if (arith && ((ts.mask >> l) & 1u)) report(P, err, ts.pos0 + l, MDIM_ERR_ARITH, I.n, 0, (uint64_t)st[D - 1][l], 0);
                 }
-                bool carry = true;  // advance the reduction coordinates, last axis fastest
-#pragma unroll
-                for (int a = MAXR - 1; a >= 0; --a) {
-                    if (carry && a >= P.rank && a < P.rank + P.red_rank) {
-                        ts.c[a] += 1;
-                        if ((uint64_t)ts.c[a] == P.length[a]) ts.c[a] = 0; else carry = false;
-                    }
-                }
+                advance_red<WIDE, MAXR>(P, ts);
                 ts.red_k += 1;
                 if (ts.red_k < P.red_count) next = I.slot;
             }
@@ -601,17 +615,56 @@ struct SigInstr { uint8_t opc, dtype, op, aux; };
 
 struct NoSig { static constexpr int n = 0; };
 
-template <class Sig, int PC, int D, class S, int V, int MAXD, bool WIDE, int MAXR>
+// index of the FOLD_STEP that closes the FOLD_BEGIN at `pc` (folds do not nest)
+template <class Sig> MDIM_CE int sig_fold_end(int pc) {
+    for (int i = pc + 1; i < Sig::n; ++i)
+        if (Sig::code[i].opc == OPC_FOLD_STEP) return i;
+    return Sig::n;
+}
+MDIM_CE int sig_depth_after(SigInstr I, int d) {
+    return d + (I.opc == OPC_LEAF_VEC || I.opc == OPC_LEAF_BCAST || I.opc == OPC_LEAF_STRIDED || I.opc == OPC_IOTA || I.opc == OPC_CONST ||
+                        I.opc == OPC_FOLD_BEGIN ? 1
+                : I.opc == OPC_BINARY || I.opc == OPC_FOLD_STEP ? -1
+                : I.opc == OPC_GATHER ? 1 - (int)I.aux
+                                      : 0);
+}
+
+// Runs instructions [PC, STOP) of the signature at compile-time depth D.  A fold becomes a real loop:
+//   FOLD_BEGIN; for k in 0..red_count { body; FOLD_STEP }   — sequential, index order (src/view.rs:250-252)
+template <class Sig, int PC, int D, int STOP, class S, int V, int MAXD, bool WIDE, int MAXR>
 MDIM_FN void run_static(const Program& P, ErrWord* err, S (&st)[MAXD][V], ThreadState<WIDE, MAXR>& ts) {
-    if constexpr (PC < Sig::n) {
+    if constexpr (PC < STOP) {
         constexpr SigInstr I = Sig::code[PC];
-        exec_instr<D, S, V, MAXD, WIDE, MAXR>(P, err, I.opc, I.dtype, I.op, I.aux, PC, st, ts);
-        constexpr int ND = D + (I.opc == OPC_LEAF_VEC || I.opc == OPC_LEAF_BCAST || I.opc == OPC_LEAF_STRIDED || I.opc == OPC_IOTA ||
-                                        I.opc == OPC_CONST ? 1
-                                : I.opc == OPC_BINARY ? -1
-                                : I.opc == OPC_GATHER ? 1 - (int)I.aux
-                                                      : 0);
-        run_static<Sig, PC + 1, ND, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
+        if constexpr (I.opc == OPC_FOLD_BEGIN) {
+            constexpr int END = sig_fold_end<Sig>(PC);
+            exec_instr<D, S, V, MAXD, WIDE, MAXR>(P, err, I.opc, I.dtype, I.op, I.aux, PC, st, ts);
+            constexpr SigInstr E = Sig::code[END < Sig::n ? END : PC];
+            // Outer loop: the slower reduction axes (coordinates in c[], rare).  Inner loop: the fastest one,
+            // where every coordinate in c[] is loop-invariant, so an operand's address is base + rk * rstride;
+            // unrolled so that several steps' loads (independent of the add chain) are in flight together.
+            const uint64_t outer = P.red_fast_len ? P.red_count / P.red_fast_len : 0;
+            for (uint64_t ko = 0; ko < outer; ++ko) {
+#pragma unroll 8
+                for (uint64_t k = 0; k < P.red_fast_len; ++k) {
+                    ts.rk = (typename CoordTraits<WIDE>::coord_t)k;
+                    run_static<Sig, PC + 1, D + 1, END, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
+                    if constexpr (D + 2 <= MAXD) {
+#pragma unroll
+                        for (int l = 0; l < V; ++l) {
+                            bool arith = false;
+                            st[D][l] = bin_op<S>(E.dtype, E.op, E.aux, st[D][l], st[D + 1][l], arith);
+                            if (arith && ((ts.mask >> l) & 1u)) report(P, err, ts.pos0 + l, MDIM_ERR_ARITH, P.instr[END].n, 0, (uint64_t)st[D + 1][l], 0);
+                        }
+                    }
+                }
+                ts.rk = 0;
+                carry_red<WIDE, MAXR>(P, ts);
+            }
+            run_static<Sig, END + 1, D + 1, STOP, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
+        } else {
+            exec_instr<D, S, V, MAXD, WIDE, MAXR>(P, err, I.opc, I.dtype, I.op, I.aux, PC, st, ts);
+            run_static<Sig, PC + 1, sig_depth_after(I, D), STOP, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
+        }
     }
 }
 
@@ -658,6 +711,7 @@ MDIM_FN void eval_vector(const Program& P, void* out, ErrWord* err, uint64_t g) 
     ts.pos0 = g * (uint64_t)(V * VPT);
     ts.mask = (1u << V) - 1u;
     ts.red_k = 0;
+    ts.rk = 0;
     coord_t rem = (coord_t)g;
 #pragma unroll
     for (int a = 0; a < MAXR - 1; ++a) {  // axis 0 = the vector axis, peeled first
@@ -672,7 +726,7 @@ MDIM_FN void eval_vector(const Program& P, void* out, ErrWord* err, uint64_t g) 
     S st[MAXD][V];
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {  // VPT consecutive vectors along the vector axis share one decode
-        if constexpr (Sig::n > 0) run_static<Sig, 0, 0, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
+        if constexpr (Sig::n > 0) run_static<Sig, 0, 0, Sig::n, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
         else run_interp<S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
         st_vector<S, V>(out, ts.pos0, esize_of(P.out_dtype), st[0], true);
         if constexpr (VPT > 1) {

@@ -265,6 +265,10 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
         A.offset = n.offset;
         for (int g = 0; g < n_axes; ++g) A.stride[pa(g)] = cstride[ni][g];
         A.inner = rank > 0 ? A.stride[0] : 0;
+        if (red_rank > 0) {  // the fastest reduction axis is walked by a dedicated counter (see exec.cuh: rk)
+            A.rstride = cstride[ni][n_axes - 1];
+            A.stride[pa(n_axes - 1)] = 0;
+        }
         *slot = P.n_addr++;
         return MDIM_OK;
     };
@@ -398,6 +402,8 @@ int Builder::emit() {
     P.rank = rank; P.red_rank = red_rank;
     P.out_dtype = e->nodes[root].dtype;
     for (int g = 0; g < n_axes; ++g) P.length[pa(g)] = len[g];
+    P.red_fast_len = 1;
+    if (red_rank > 0) { P.red_fast_len = len[n_axes - 1]; P.length[pa(n_axes - 1)] = 1; }
     uint64_t out_elems = 1, red_count = 1;
     for (int g = 0; g < rank; ++g) out_elems *= len[g];
     for (int g = rank; g < n_axes; ++g) red_count *= len[g];
@@ -420,6 +426,15 @@ int Builder::emit() {
         const int* cand = slot == 4 ? cand32 : cand64;
         for (int i = 0; i < 3; ++i)
             if (len[rank - 1] % (uint64_t)cand[i] == 0) { V = cand[i]; break; }
+    }
+    // A fold walks its reduction axes sequentially inside one thread, so the output is the only source of
+    // parallelism: prefer narrower vectors until there are enough threads to fill the machine.
+    if (fold_node >= 0 && rank > 0) {
+        const int cand32[3] = {8, 4, 1}, cand64[3] = {4, 2, 1};
+        const int* cand = slot == 4 ? cand32 : cand64;
+        static const uint64_t min_threads = [] { const char* e = getenv("MDIM_FOLD_MIN_THREADS"); return e ? (uint64_t)atoll(e) : 40000ull; }();  // measured: 64 Ki threads x 16 B beat 256 Ki x 4 B and 32 Ki x 32 B
+        for (int i = 0; i < 3 && out_elems / (uint64_t)V < min_threads; ++i)
+            if (cand[i] < V && len[rank - 1] % (uint64_t)cand[i] == 0) V = cand[i];
     }
     if (force_vec) V = force_vec;
     // Vectors per thread trip along the vector axis.  Measured on B200 (round 1): 4 consecutive vectors per

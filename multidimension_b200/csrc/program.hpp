@@ -52,6 +52,7 @@ struct Addr {
     int64_t offset;             // elements
     int64_t stride[kMaxRank];   // elements per unit of each (coalesced) iteration axis
     int64_t inner;              // stride along the innermost OUTPUT axis (the vector axis)
+    int64_t rstride;            // stride along the FASTEST reduction axis (walked by ThreadState::rk, not by c[])
     int64_t gstride[kMaxComp];  // GATHER: elements per unit of index component
     uint64_t bound[kMaxComp];   // GATHER: size of index component
     int32_t n_peers;            // GATHER over peer-mapped shards (see mdim_node.n_peers)
@@ -91,6 +92,7 @@ struct Program {
     uint32_t div_shr[kMaxRank];
     uint64_t n_vec;             // total output vectors = prod(out lengths) / vec
     uint64_t red_count;         // prod(reduction lengths)
+    uint64_t red_fast_len;      // length of the fastest reduction axis (its entry in length[] is 1, its stride[] entries 0)
     uint64_t explain_pos;       // PF_EXPLAIN: output position whose failure details to record
     Instr instr[kMaxInstr];
     Addr addr[kMaxAddr];

@@ -24,6 +24,8 @@ namespace mdim {
 #define I_SELECT(dt) {OPC_SELECT, dt, 0, 0}
 #define I_GATHER1(dt) {OPC_GATHER, dt, 0, 1}
 #define I_IOTA(dt) {OPC_IOTA, dt, 0, 0}
+#define I_FOLD_BEGIN(dt) {OPC_FOLD_BEGIN, dt, 0, 0}
+#define I_FOLD_STEP(dt, op) {OPC_FOLD_STEP, dt, op, dt}
 
 // ---- 32-bit slot programs (f32) ----------------------------------------------------------------
 MDIM_SIG(SigCopyF32, I_LV(MDIM_F32))
@@ -52,6 +54,13 @@ MDIM_SIG(SigDiagMulAddCF32, I_LB(MDIM_F32), I_SELECT(MDIM_F32), I_LVC(MDIM_F32),
          I_BIN(MDIM_F32, MDIM_ADD))
 // v.diagonal(zero) of a vector or matrix (inner axis broadcast or strided is interpreted; this is the LB form)
 MDIM_SIG(SigDiagF32, I_LB(MDIM_F32), I_SELECT(MDIM_F32))
+
+// rows().map(|r| fold r.each(..)) over any axis that is not a contiguous last axis (that shape has its own
+// kernel, k_fold_rows): a fold over the OUTERMOST axis (vector loads, e.g. the per-rank partial of a
+// sharded-axis reduction) and over a strided axis.  The loop is a real loop, sequential, in index order.
+MDIM_SIG(SigFoldAddVecF32, I_FOLD_BEGIN(MDIM_F32), I_LV(MDIM_F32), I_FOLD_STEP(MDIM_F32, MDIM_ADD))
+MDIM_SIG(SigFoldAddStridedF32, I_FOLD_BEGIN(MDIM_F32), I_LS(MDIM_F32), I_FOLD_STEP(MDIM_F32, MDIM_ADD))
+MDIM_SIG(SigFoldMulVecF32, I_FOLD_BEGIN(MDIM_F32), I_LV(MDIM_F32), I_FOLD_STEP(MDIM_F32, MDIM_MUL))
 
 // ---- 64-bit slot programs ----------------------------------------------------------------------
 MDIM_SIG(SigCopyU64, I_LV(MDIM_U64))

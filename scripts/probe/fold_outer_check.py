@@ -16,4 +16,12 @@ for (I, J, K) in [(16, 32, 64), (64, 256, 64), (512, 1024, 256), (512, 64, 64), 
     torch.cuda.synchronize()
     ref = t.view(I, J * K).double().sum(dim=0)
     rel = ((tp.double() - ref).abs() / ref.abs())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o = Storage.wrap_device(ctx, F.F32, J * K, tp.data_ptr(), keep=tp)
+    e0.record(stream)
+    for _ in range(5):
+        v.collect(out=o, flags=F.COLLECT_ASYNC)
+    e1.record(stream); torch.cuda.synchronize(); ctx.sync()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"{ms:.4f} ms {4 * I * J * K / ms / 1e6:.0f} GB/s", end=" ")
     print((I, J, K), v.describe(), "max rel", rel.max().item(), "bad", int((rel > 1e-5).sum()), "first bad", int(torch.nonzero(rel > 1e-5)[0]) if (rel > 1e-5).any() else -1)

@@ -230,6 +230,19 @@ def test_fold_other_ops_and_types(ctx):
     check(fold_rows(f, (), (usize, usize), Add, np.float32(0)), ctx)                                               # full reduction
 
 
+@pytest.mark.parametrize("shape", [(64, 40, 64), (7, 3, 8), (300, 5, 12), (33, 17, 1)])
+def test_fold_over_outermost_axis(ctx, shape):  # the per-rank partial of a sharded-axis reduction
+    rng = np.random.default_rng(sum(shape))
+    I, J, K = shape
+    a = Array.new((usize, usize, usize), shape, rng.uniform(0, 1, I * J * K).astype(np.float32))
+    v = fold_rows(a.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize)), (usize, usize), usize, Add, np.float32(0))
+    check(v, ctx)
+    check(v, ctx, F.COLLECT_NO_STATIC)
+    seq = np.add.accumulate(a.as_ref().reshape(I, J * K), axis=0, dtype=np.float32)[-1]
+    assert_same_bits(collect(v, ctx), seq)
+    check(fold_rows(a.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize)), (usize, usize), usize, Mul, np.float32(1)), ctx)
+
+
 # ---- K5: general rank-N evaluator (config 5) ----------------------------------------------------------------------------
 def config5(P_, Q, R, rng):
     a = Array.new((usize, usize), (P_, Q), rand(rng, "f32", P_ * Q))
