@@ -98,7 +98,8 @@ typedef enum mdim_node_kind {
     MDIM_NODE_DIAG = 5,   /* Diagonal<V>: src/view.rs:846-857                                       */
     MDIM_NODE_GATHER = 6, /* Compose<V,W>: src/view.rs:897-912; MapAxis: src/view.rs:1140-1170      */
     MDIM_NODE_FOLD = 7,   /* rows().map(|r| fold r.each(..)): src/view.rs:617-622,1330-1342,250-252 */
-    MDIM_NODE_KIND_COUNT = 8
+    MDIM_NODE_CONCAT = 8, /* Concat<V,W,I,J>: src/view.rs:920-946 (coord[axis_a[0]] < axis_c[0] ? V : W)  */
+    MDIM_NODE_KIND_COUNT = 9
 } mdim_node_kind;
 
 typedef union mdim_scalar {
@@ -114,7 +115,7 @@ typedef union mdim_scalar {
 /*
  * One node of the expression, nodes are stored in POST-ORDER (children before parent, left to
  * right), so the array is also a stack program.  Arity: LEAF/IOTA/CONST 0, UNARY 1, BINARY 2,
- * DIAG 1, GATHER n_comp, FOLD 1.  The last node is the root and its dtype is the output dtype.
+ * DIAG 1, GATHER n_comp, FOLD 1, CONCAT 2.  The last node is the root and its dtype is the output dtype.
  *
  * Iteration axes: 0..rank-1 are the output leaf axes, rank..rank+red_rank-1 the reduction axes.
  * Only nodes below a FOLD may have non-zero strides on reduction axes.
@@ -134,9 +135,11 @@ typedef struct mdim_node {
                                        0 = operand lacks the axis (Broadcast, src/broadcast.rs:46-60) */
     int64_t gstride[MDIM_MAX_RANK]; /* GATHER: elements per unit of index component c */
     uint64_t bound[MDIM_MAX_RANK];  /* GATHER: size of component c; idx >= bound is MDIM_ERR_OOB */
-    int32_t axis_a[MDIM_MAX_RANK];  /* DIAG pair p: iteration axis on the left ...                  */
+    int32_t axis_a[MDIM_MAX_RANK];  /* DIAG pair p: iteration axis on the left ... (CONCAT: [0] = the axis) */
     int32_t axis_b[MDIM_MAX_RANK];  /* ... equals iteration axis on the right, or, if axis_b[p] < 0, */
-    uint64_t axis_c[MDIM_MAX_RANK]; /* ... equals the constant axis_c[p] (a Row/Column of a Diagonal) */
+    uint64_t axis_c[MDIM_MAX_RANK]; /* ... equals the constant axis_c[p] (a Row/Column of a Diagonal);
+                                       CONCAT: [0] = length of V along the axis; W's strides are already
+                                       expressed against the concatenated coordinate (offset shifted) */
     mdim_scalar imm;                /* CONST value; DIAG `zero`; FOLD init */
     const void* peer[MDIM_MAX_PEERS];
     uint64_t peer_block;

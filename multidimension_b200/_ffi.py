@@ -27,7 +27,7 @@ ADD, SUB, MUL, DIV, REM, AND, OR, XOR, SHL, SHR = range(10)
 # unary ops (mdim_unary_op)
 NEG, NOT, ABS, SQRT, CAST = range(5)
 # node kinds
-LEAF, IOTA, CONST, UNARY, BINARY, DIAG, GATHER, FOLD = range(8)
+LEAF, IOTA, CONST, UNARY, BINARY, DIAG, GATHER, FOLD, CONCAT = range(9)
 
 COLLECT_ASYNC, COLLECT_NO_FASTPATH, COLLECT_NO_STATIC = 1, 2, 4
 IPC_HANDLE_BYTES = 64

@@ -518,14 +518,51 @@ struct HostBuf {       // one distinct host operand (several nodes may view the 
 
 struct NodeRange { int64_t lo, hi; };  // [lo, hi) over all coordinates, relative to element 0 of the buffer
 
+// Per node, the coordinate range [lo, hi) of every iteration axis over which the node is evaluated: the
+// whole axis, except under a CONCAT, whose V side sees [0, len(V)) and whose W side [len(V), end).
+struct AxisRange { uint64_t lo[MDIM_MAX_RANK], hi[MDIM_MAX_RANK]; };
+
+void node_axis_ranges(const mdim_expr* e, std::vector<AxisRange>& out) {
+    const int total = e->rank + e->red_rank;
+    out.assign(e->n_nodes, AxisRange{});
+    std::vector<std::vector<int>> kids(e->n_nodes);
+    std::vector<int> stack;
+    for (int i = 0; i < e->n_nodes; ++i) {
+        const mdim_node& n = e->nodes[i];
+        int k = 0;
+        switch (n.kind) {
+            case MDIM_NODE_UNARY: case MDIM_NODE_DIAG: case MDIM_NODE_FOLD: k = 1; break;
+            case MDIM_NODE_BINARY: case MDIM_NODE_CONCAT: k = 2; break;
+            case MDIM_NODE_GATHER: k = n.n_comp; break;
+            default: k = 0;
+        }
+        for (int c = 0; c < k; ++c) kids[i].push_back(stack[stack.size() - k + c]);
+        stack.resize(stack.size() - k);
+        stack.push_back(i);
+    }
+    for (int a = 0; a < total; ++a) { out[e->n_nodes - 1].lo[a] = 0; out[e->n_nodes - 1].hi[a] = e->length[a]; }
+    for (int i = e->n_nodes - 1; i >= 0; --i) {  // parents before children in reverse post-order
+        const mdim_node& n = e->nodes[i];
+        for (size_t c = 0; c < kids[i].size(); ++c) {
+            AxisRange r = out[i];
+            if (n.kind == MDIM_NODE_CONCAT) {
+                const int a = n.axis_a[0];
+                if (c == 0) r.hi[a] = std::min<uint64_t>(r.hi[a], n.axis_c[0]);
+                else r.lo[a] = std::max<uint64_t>(r.lo[a], n.axis_c[0]);
+            }
+            out[kids[i][c]] = r;
+        }
+    }
+}
+
 // reach of offset + sum(coord[a] * stride[a]) over axes [first, total) (+ gather components)
-NodeRange node_reach(const mdim_expr* e, const mdim_node& n, int first) {
+NodeRange node_reach(const mdim_expr* e, const mdim_node& n, const AxisRange& r, int first) {
     int64_t lo = n.offset, hi = n.offset;
     const int total = e->rank + e->red_rank;
     for (int a = first; a < total; ++a) {
-        if (e->length[a] == 0) continue;
-        const int64_t span = (int64_t)(e->length[a] - 1) * n.stride[a];
-        if (span > 0) hi += span; else lo += span;
+        if (r.hi[a] <= r.lo[a]) continue;  // never evaluated along this axis: contributes nothing
+        const int64_t s0 = (int64_t)r.lo[a] * n.stride[a], s1 = (int64_t)(r.hi[a] - 1) * n.stride[a];
+        lo += std::min(s0, s1); hi += std::max(s0, s1);
     }
     if (n.kind == MDIM_NODE_GATHER)
         for (int c = 0; c < n.n_comp; ++c) {
@@ -585,8 +622,11 @@ extern "C" int mdim_collect_host(mdim_ctx* ctx, const mdim_expr* e, void* out_ho
     std::vector<HostBuf> bufs;
     std::vector<int> node_buf(e->n_nodes, -1);
     bool can_chunk = e->rank >= 1 && n0 >= 2;
+    std::vector<AxisRange> ranges;
+    node_axis_ranges(e, ranges);
     for (int i = 0; i < e->n_nodes; ++i) {
         const mdim_node& n = e->nodes[i];
+        if (n.kind == MDIM_NODE_CONCAT && n.axis_a[0] == 0) can_chunk = false;  // range test on the chunked coordinate
         if (n.kind == MDIM_NODE_DIAG) {
             for (int p = 0; p < n.n_comp; ++p)
                 if (n.axis_a[p] == 0 || n.axis_b[p] == 0) can_chunk = false;  // predicate on the chunked coordinate
@@ -594,12 +634,12 @@ extern "C" int mdim_collect_host(mdim_ctx* ctx, const mdim_expr* e, void* out_ho
         }
         if (n.kind != MDIM_NODE_LEAF && n.kind != MDIM_NODE_GATHER) continue;
         if (n.kind == MDIM_NODE_GATHER && n.n_peers > 1) return set_error(ctx, MDIM_ERR_INVALID, "peer-sharded gather source in a host collect");
-        const NodeRange all = node_reach(e, n, 0);
+        const NodeRange all = node_reach(e, n, ranges[i], 0);
         int b = -1;
         for (size_t k = 0; k < bufs.size(); ++k) if (bufs[k].base == (const char*)n.data) b = (int)k;
         const int es = dtype_size(n.dtype);
         const bool slabbed = n.kind == MDIM_NODE_LEAF && n.stride[0] > 0;
-        NodeRange slab = slabbed ? node_reach(e, n, 1) : NodeRange{0, 0};
+        NodeRange slab = slabbed ? node_reach(e, n, ranges[i], 1) : NodeRange{0, 0};
         bool disjoint = slabbed && slab.hi - slab.lo <= n.stride[0];
         for (int a = 1; a < total && disjoint; ++a) if (n.stride[a] < 0) disjoint = false;
         if (b < 0) {

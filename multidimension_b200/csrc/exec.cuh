@@ -417,12 +417,15 @@ MDIM_FN uint32_t eval_preds(const Program& P, const ThreadState<WIDE, MAXR>& ts,
 #pragma unroll
         for (int a = 0; a < MAXR; ++a) s += (off_t)ts.c[a] * (off_t)P.pred[p].coef[a];
         const off_t rhs = (off_t)P.pred[p].rhs, lc = (off_t)P.pred[p].lane_coef;
+        const int cmp = P.pred[p].cmp;  // 0: ==   1: <   2: >=
         if (lc == 0) {  // the vector axis is not involved: one test for all lanes
-            if (s != rhs) m = 0;
+            if (!(cmp == 0 ? s == rhs : cmp == 1 ? s < rhs : s >= rhs)) m = 0;
         } else {
 #pragma unroll
-            for (int l = 0; l < V; ++l)
-                if (s + (off_t)l * lc != rhs) m &= ~(1u << l);
+            for (int l = 0; l < V; ++l) {
+                const off_t x = s + (off_t)l * lc;
+                if (!(cmp == 0 ? x == rhs : cmp == 1 ? x < rhs : x >= rhs)) m &= ~(1u << l);
+            }
         }
     }
     return m;
@@ -440,7 +443,7 @@ MDIM_FN void report(const Program& P, ErrWord* err, uint64_t pos, int status, in
 MDIM_FN int depth_delta(int opc, int aux) {
     switch (opc) {
         case OPC_LEAF_VEC: case OPC_LEAF_BCAST: case OPC_LEAF_STRIDED: case OPC_IOTA: case OPC_CONST: case OPC_FOLD_BEGIN: return 1;
-        case OPC_BINARY: case OPC_FOLD_STEP: return -1;
+        case OPC_BINARY: case OPC_FOLD_STEP: case OPC_SELECT2: return -1;
         case OPC_GATHER: return 1 - aux;
         default: return 0;
     }
@@ -511,13 +514,19 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
         case OPC_LEAF_VEC:  // Array::at = items[to_usize(index)] (src/array.rs:81,86), V at a time
             if constexpr (D < MAXD) {
                 const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts);
-                if (aux) ld_vector<S, V, true>(P.addr[I.slot].ptr, off, esize_of(dtype), st[D]);   // re-read operand: keep in L1
-                else ld_vector<S, V, false>(P.addr[I.slot].ptr, off, esize_of(dtype), st[D]);      // read once: stream past L1
+                if (ts.mask == (1u << V) - 1u) {  // (a compile-time fact in signatures without MASK)
+                    if (aux) ld_vector<S, V, true>(P.addr[I.slot].ptr, off, esize_of(dtype), st[D]);   // re-read operand: keep in L1
+                    else ld_vector<S, V, false>(P.addr[I.slot].ptr, off, esize_of(dtype), st[D]);      // read once: stream past L1
+                } else {  // under a Concat / lazy Diagonal: inactive lanes must not touch memory
+                    const int es = esize_of(dtype);
+#pragma unroll
+                    for (int l = 0; l < V; ++l) st[D][l] = ((ts.mask >> l) & 1u) ? ld_scalar<S>(P.addr[I.slot].ptr, off + l, es) : (S)0;
+                }
             }
             break;
         case OPC_LEAF_BCAST:  // operand lacks the vector axis: Broadcast::index drops it (src/broadcast.rs:46-60)
             if constexpr (D < MAXD) {
-                const S v = ld_scalar<S>(P.addr[I.slot].ptr, (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts), esize_of(dtype));
+                const S v = ts.mask ? ld_scalar<S>(P.addr[I.slot].ptr, (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts), esize_of(dtype)) : (S)0;
 #pragma unroll
                 for (int l = 0; l < V; ++l) st[D][l] = v;
             }
@@ -527,7 +536,7 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
                 const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts), s_in = inner_stride(P, I.slot);
                 const int es = esize_of(dtype);
 #pragma unroll
-                for (int l = 0; l < V; ++l) st[D][l] = ld_scalar<S>(P.addr[I.slot].ptr, off + (int64_t)l * s_in, es);
+                for (int l = 0; l < V; ++l) st[D][l] = ((ts.mask >> l) & 1u) ? ld_scalar<S>(P.addr[I.slot].ptr, off + (int64_t)l * s_in, es) : (S)0;
             }
             break;
         case OPC_IOTA:  // All<I>::at(index) = index (src/index.rs:185)
@@ -571,6 +580,13 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
                 const uint32_t m = eval_preds<V, WIDE, MAXR>(P, ts, I.slot, I.n);
 #pragma unroll
                 for (int l = 0; l < V; ++l) st[D - 1][l] = ((m >> l) & 1u) ? st[D - 1][l] : (S)I.imm;
+            }
+            break;
+        case OPC_SELECT2:  // Concat::at (src/view.rs:938-945): V where coord < len(V), else W
+            if constexpr (D >= 2) {
+                const uint32_t m = eval_preds<V, WIDE, MAXR>(P, ts, I.slot, 1);
+#pragma unroll
+                for (int l = 0; l < V; ++l) st[D - 2][l] = ((m >> l) & 1u) ? st[D - 2][l] : st[D - 1][l];
             }
             break;
         case OPC_GATHER:
@@ -624,7 +640,7 @@ template <class Sig> MDIM_CE int sig_fold_end(int pc) {
 MDIM_CE int sig_depth_after(SigInstr I, int d) {
     return d + (I.opc == OPC_LEAF_VEC || I.opc == OPC_LEAF_BCAST || I.opc == OPC_LEAF_STRIDED || I.opc == OPC_IOTA || I.opc == OPC_CONST ||
                         I.opc == OPC_FOLD_BEGIN ? 1
-                : I.opc == OPC_BINARY || I.opc == OPC_FOLD_STEP ? -1
+                : I.opc == OPC_BINARY || I.opc == OPC_FOLD_STEP || I.opc == OPC_SELECT2 ? -1
                 : I.opc == OPC_GATHER ? 1 - (int)I.aux
                                       : 0);
 }

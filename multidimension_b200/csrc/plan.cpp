@@ -48,7 +48,7 @@ static int node_arity(const mdim_node& n) {
     switch (n.kind) {
         case MDIM_NODE_LEAF: case MDIM_NODE_IOTA: case MDIM_NODE_CONST: return 0;
         case MDIM_NODE_UNARY: case MDIM_NODE_DIAG: case MDIM_NODE_FOLD: return 1;
-        case MDIM_NODE_BINARY: return 2;
+        case MDIM_NODE_BINARY: case MDIM_NODE_CONCAT: return 2;
         case MDIM_NODE_GATHER: return n.n_comp;
     }
     return -1;
@@ -155,6 +155,10 @@ int Builder::validate() {
                 }
                 break;
             }
+            case MDIM_NODE_CONCAT:
+                if (e->nodes[child[i][0]].dtype != n.dtype || e->nodes[child[i][1]].dtype != n.dtype) return why.fail(MDIM_ERR_INVALID, "node %d: concat dtype mismatch", i);
+                if (n.axis_a[0] < 0 || n.axis_a[0] >= total) return why.fail(MDIM_ERR_INVALID, "node %d: bad concat axis", i);
+                break;
             case MDIM_NODE_DIAG:
                 if (e->nodes[child[i][0]].dtype != n.dtype) return why.fail(MDIM_ERR_INVALID, "node %d: diag dtype mismatch", i);
                 if (n.n_comp < 0 || n.n_comp > kMaxRank) return why.fail(MDIM_ERR_INVALID, "node %d: bad pair count", i);
@@ -191,6 +195,7 @@ void Builder::canonical_axes() {
     bool pred_axis[kMaxRank] = {false};
     for (int i = 0; i < e->n_nodes; ++i) {
         const mdim_node& n = e->nodes[i];
+        if (n.kind == MDIM_NODE_CONCAT) pred_axis[n.axis_a[0]] = true;
         if (n.kind != MDIM_NODE_DIAG) continue;
         for (int p = 0; p < n.n_comp; ++p) {
             pred_axis[n.axis_a[p]] = true;
@@ -244,7 +249,7 @@ int Builder::push_instr(const Instr& in) {
     P.instr[P.n_instr++] = in;
     depth += in.opc == OPC_LEAF_VEC || in.opc == OPC_LEAF_BCAST || in.opc == OPC_LEAF_STRIDED || in.opc == OPC_IOTA || in.opc == OPC_CONST ||
                      in.opc == OPC_FOLD_BEGIN ? 1
-             : in.opc == OPC_BINARY || in.opc == OPC_FOLD_STEP ? -1
+             : in.opc == OPC_BINARY || in.opc == OPC_FOLD_STEP || in.opc == OPC_SELECT2 ? -1
              : in.opc == OPC_GATHER ? 1 - (int)in.aux
                                     : 0;
     max_depth = std::max(max_depth, depth);
@@ -350,6 +355,32 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
                 return push_instr(m);
             }
             return MDIM_OK;
+        }
+        case MDIM_NODE_CONCAT: {
+            // Each side is evaluated under a lane mask (enclosing predicates + its own range test): its loads
+            // would otherwise run past the end of the other operand.  src/view.rs:938-945.
+            if (P.n_pred + 2 * (mask_n + 1) > kMaxPred) return why.fail(MDIM_ERR_UNSUPPORTED, "too many predicates");
+            const int axis = pa(axis_map[n.axis_a[0]]);
+            int first[2];
+            for (int side = 0; side < 2; ++side) {
+                first[side] = P.n_pred;
+                for (int p = 0; p < mask_n; ++p) P.pred[P.n_pred++] = P.pred[mask_first + p];
+                Pred pr; memset(&pr, 0, sizeof pr);
+                pr.coef[axis] = 1; pr.rhs = (int64_t)std::min<uint64_t>(n.axis_c[0], len[axis_map[n.axis_a[0]]]); pr.cmp = side == 0 ? 1 : 2;
+                pr.lane_coef = rank > 0 ? pr.coef[0] : 0;
+                P.pred[P.n_pred++] = pr;
+            }
+            for (int side = 0; side < 2; ++side) {
+                Instr m; memset(&m, 0, sizeof m);
+                m.opc = OPC_MASK; m.slot = (uint16_t)first[side]; m.n = (uint16_t)(mask_n + 1);
+                int st = push_instr(m); if (st) return st;
+                st = gen(child[ni][side], first[side], mask_n + 1); if (st) return st;
+            }
+            Instr m; memset(&m, 0, sizeof m);
+            m.opc = OPC_MASK; m.slot = (uint16_t)mask_first; m.n = (uint16_t)mask_n;
+            int st = push_instr(m); if (st) return st;
+            in.opc = OPC_SELECT2; in.slot = (uint16_t)(first[0] + mask_n);
+            return push_instr(in);
         }
         case MDIM_NODE_GATHER: {
             for (int c = 0; c < n.n_comp; ++c) { int st = gen(child[ni][c], mask_first, mask_n); if (st) return st; }

@@ -30,6 +30,7 @@ enum Opc : uint8_t {
     OPC_BINARY,
     OPC_MASK,           // set the lane-active mask from pred[slot .. slot+n)  (n = 0: all active)
     OPC_SELECT,         // Diagonal: keep TOS where pred[slot .. slot+n) holds, else imm
+    OPC_SELECT2,        // Concat: pops W (TOS) and V; keeps V where pred[slot] holds, else W
     OPC_GATHER,         // pops aux index components, bounds-checks, loads
     OPC_FOLD_BEGIN,     // push acc = imm, reset reduction coordinates
     OPC_FOLD_STEP,      // acc = acc (op) TOS; advance reduction coords; loop to pc = slot
@@ -59,9 +60,11 @@ struct Addr {
     int32_t pad;
 };
 
-struct Pred {  // sum_a coef[a] * coord[a] (+ lane * lane_coef) == rhs
+struct Pred {  // sum_a coef[a] * coord[a] (+ lane * lane_coef)  ==  rhs   (cmp 0: Diagonal)
+               //                                              <   rhs   (cmp 1: Concat, V side)
+               //                                              >=  rhs   (cmp 2: Concat, W side)
     int32_t coef[kMaxRank];
-    int32_t lane_coef, pad;  // coef of the innermost output axis
+    int32_t lane_coef, cmp;  // lane_coef: coef of the innermost output axis
     int64_t rhs;
 };
 

@@ -136,6 +136,14 @@ def substitute(node, table, memo=None):
             out = kids[0]
         else:
             out = node.clone(pairs=tuple(pairs), children=kids)
+    elif node.kind == F.CONCAT and node.pairs[0][0] in table:
+        sub, thr = table[node.pairs[0][0]], node.pairs[0][1]
+        if not sub.terms:  # the concatenated axis has been pinned (row/column): one side survives
+            out = kids[0] if sub.const < thr else kids[1]
+        elif len(sub.terms) == 1 and sub.terms[0][1] == 1:  # k = k' + const:  k < thr  <=>  k' < thr - const
+            out = node.clone(pairs=((sub.terms[0][0], max(thr - sub.const, 0)),), children=kids)
+        else:
+            raise Unsupported("a Concat whose axis has been split needs device div/mod")
     elif node.kind == F.FOLD and any(a in table for a in node.red_axes):
         raise Unsupported("substitution of a reduction axis")
     elif changed:
@@ -242,6 +250,9 @@ def emit(root, axes, location):
                 else:
                     d.axis_b[p] = pos[b]
             d.imm.u64 = imm_bits(n.dtype, n.imm)
+        if n.kind == F.CONCAT:
+            d.axis_a[0] = pos[n.pairs[0][0]]
+            d.axis_c[0] = n.pairs[0][1]
         if n.kind in (F.CONST, F.FOLD):
             d.imm.u64 = imm_bits(n.dtype, n.imm)
     e = F.Expr()

@@ -252,7 +252,7 @@ class View:
         return Compose(self, other)
 
     def concat(self, other, I, J):  # :327
-        raise Unsupported("concat is not lowered to the device yet (SURVEY.md §8f N2)")
+        return Concat(self, other, I, J)
 
     def from_usize(self, I, Xt, J, from_length):  # :352
         return FromUsize(self, I, Xt, J, from_length)
@@ -594,7 +594,7 @@ def _gather(node, table, memo):
     k = node.kind
     if k == F.CONST:
         out = node
-    elif k in (F.UNARY, F.BINARY):
+    elif k in (F.UNARY, F.BINARY) or (k == F.CONCAT and node.pairs[0][0] not in table):
         out = node.clone(children=tuple(_gather(c, table, memo) for c in node.children))
     elif k in (F.LEAF, F.GATHER):
         kids = [_gather(c, table, memo) for c in node.children]
@@ -800,6 +800,41 @@ class Columns(View):  # src/view.rs:647-652, 1376-1390
 
     def _lower(self):
         raise Unsupported("a view of views has no device representation")
+
+
+class Concat(View):  # src/view.rs:327-339, 920-946
+    def __init__(self, v, w, I, J):
+        for x in (v, w):
+            if not X.isomorphic(x.I, (I, usize, J)):
+                raise X.IndexError_(f"concat: {x.I!r} is not isomorphic to {(I, usize, J)!r}")
+        if not _same_T(v.T, w.T):
+            raise TypeError("concat: element types differ")
+        vi, self._nv, vj = X.to_iso_size(v._size, v.I, (I, usize, J))
+        wi, nw, wj = X.to_iso_size(w._size, w.I, (I, usize, J))
+        if vi != wi:  # assert_eq!(self_i, other_i), :336
+            raise Panic(F.ERR_SIZE, f"assertion `left == right` failed\n  left: {vi!r}\n right: {wi!r}")
+        if vj != wj:  # assert_eq!(self_j, other_j), :337
+            raise Panic(F.ERR_SIZE, f"assertion `left == right` failed\n  left: {vj!r}\n right: {wj!r}")
+        self.v, self.w, self._parts, self.T = v, w, (I, J), v.T
+        self.I, self._size = (I, usize, J), (vi, self._nv + nw, vj)
+
+    def _lower(self):
+        I, J = self._parts
+        gv, value_v = self.v._lower()
+        gw, value_w = self.w._lower()
+        vi, vk, vj = _split_groups(gv, I, usize, J)
+        wi, wk, wj = _split_groups(gw, I, usize, J)
+        if len(vk[0]) != 1 or len(wk[0]) != 1:
+            raise Unsupported("concat along an axis that is a merged group (to_usize) needs device div/mod")
+        K = L.Axis(self._size[1])
+        table_v = {vk[0][0]: L.Sub(0, ((K, 1),))}
+        table_w = {a: L.Sub(0, ((b, 1),)) for a, b in zip(_flat(wi) + _flat(wj), _flat(vi) + _flat(vj))}
+        table_w[wk[0][0]] = L.Sub(-self._nv, ((K, 1),))  # W is addressed with k - len(V), :943
+        sv, sw = _substituter(table_v), _substituter(table_w)
+        lv, lw = L.flatten_value(value_v), L.flatten_value(value_w)
+        out = [L.Node(F.CONCAT, a.dtype, children=(sv(a), sw(b)), pairs=((K, self._nv),)) for a, b in zip(lv, lw)]
+        value = _build_like(self.T, list(out)) if isinstance(self.T, tuple) else out[0]
+        return vi + [[K]] + vj, value
 
 
 class FromUsize(View):  # src/view.rs:352-363, 993-1021

@@ -51,7 +51,7 @@ static int arity(const mdim_node* n) {
     switch (n->kind) {
         case MDIM_NODE_LEAF: case MDIM_NODE_IOTA: case MDIM_NODE_CONST: return 0;
         case MDIM_NODE_UNARY: case MDIM_NODE_DIAG: case MDIM_NODE_FOLD: return 1;
-        case MDIM_NODE_BINARY: return 2;
+        case MDIM_NODE_BINARY: case MDIM_NODE_CONCAT: return 2;
         case MDIM_NODE_GATHER: return n->n_comp;
     }
     return -1;
@@ -312,6 +312,9 @@ static mdim_scalar at(oracle_t* o, int ni) {
             }
             return at(o, o->child[ni][0]);
         }
+        case MDIM_NODE_CONCAT: /* src/view.rs:938-945: only the selected side is evaluated */
+            if (o->coord[n->axis_a[0]] < n->axis_c[0]) return at(o, o->child[ni][0]);
+            return at(o, o->child[ni][1]);
         case MDIM_NODE_GATHER: { /* src/view.rs:905,911: w.at(v.at(i)); bounds per component src/int.rs:16-19 */
             int64_t idx = linear(o, n);
             for (int c = 0; c < n->n_comp; ++c) {

@@ -280,6 +280,30 @@ def test_mixed_strides_broadcast(ctx):
     check(a.column((usize, usize), usize, 5), ctx)
 
 
+def test_concat_along_every_axis(ctx):  # src/view.rs:920-946
+    rng = np.random.default_rng(13)
+    x = Array.new((usize, usize), (50, 16), rand(rng, "f32", 800))
+    y = Array.new((usize, usize), (50, 24), rand(rng, "f32", 1200))
+    c = x.concat(y, usize, ())                      # along the innermost (vector) axis
+    check(c, ctx)
+    check(c.transpose((), usize, usize, ()), ctx)
+    ci = c.iso((usize, usize))                      # ((),()) does not broadcast in the reference, so regroup first
+    check(ci * ci + Scalar(1.0, "f32"), ctx)
+    check(c.column(usize, usize, 20), ctx)          # pinned inside W: only W survives the lowering
+    check(c.row(usize, usize, 7), ctx)
+    x2 = Array.new((usize, usize), (30, 40), rand(rng, "f32", 1200))
+    y2 = Array.new((usize, usize), (70, 40), rand(rng, "f32", 2800))
+    c2 = x2.concat(y2, (), usize)                   # along the outermost axis
+    check(c2, ctx)
+    check(c2.concat(c2, (), usize), ctx)            # nested concats
+    odd = Array.new(usize, 13, rand(rng, "f32", 13)).concat(Array.new(usize, 30, rand(rng, "f32", 30)), (), ())
+    check(odd, ctx)                                 # boundary inside a vector: per-lane masked loads
+    # laziness: the side that is not selected is never evaluated (an out-of-range index there is harmless)
+    src = Array.new(usize, 4, np.float32([10, 11, 12, 13]))
+    good = Array.new(usize, 3, np.uint64([3, 2, 1])).compose(src)
+    check(good.concat(Array.new(usize, 5, rand(rng, "f32", 5)), (), ()), ctx)
+
+
 # ---- host-buffer entry point (mdim_collect_host) ------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_collect_host_chunked():
@@ -306,6 +330,9 @@ def test_collect_host_chunked():
                  fold_rows(m, usize, usize, Add, np.float32(0)),
                  m - (fold_rows(m, usize, usize, Add, np.float32(0)) / Scalar(700.0, "f32")).iso((usize, ()))):
         assert_same_bits(view.collect(ctx=c2).as_ref(), oracle_collect(view), str(view.describe()))
+    m2 = Array.new((usize, usize), (3000, 300), rand(rng, "f32", 3000 * 300))
+    for view in (m.concat(m2, usize, ()), m.concat(m, (), usize), m.concat(m2, usize, ()).transpose((), usize, usize, ())):
+        assert_same_bits(view.collect(ctx=c2).as_ref(), oracle_collect(view), "host concat " + str(view.describe()))
     src = Array.new(usize, 5000, rand(rng, "f32", 5000))
     iv = rng.integers(0, 5000, 1 << 19).astype(np.uint64)
     idx = Array.new(usize, iv.size, iv)

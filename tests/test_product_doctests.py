@@ -83,6 +83,16 @@ def test_compose_out_of_bounds(run):  # src/int.rs:17 panic text
         run(a.compose(b))
 
 
+def test_concat(golden, run):  # src/view.rs:320-326
+    a = Array.new(usize, 2, enc(["apple", "body"]))
+    b = Array.new(usize, 2, enc(["crane", "dump"]))
+    ab = a.concat(b, (), ()).iso(usize)
+    assert ab.size() == 4
+    assert words(run(ab)) == exp(golden, "concat")
+    with pytest.raises(P.Panic):  # src/view.rs:336-337: outer / inner sizes must agree
+        Array.new((usize, usize), (2, 3), list(range(6))).concat(Array.new((usize, usize), (2, 4), list(range(8))), (), usize)
+
+
 def test_from_usize_to_usize(golden, run):  # src/view.rs:346-351, 367-372
     g = golden["from_usize"]
     a = Array.new((usize, usize, usize), (3, 2, 1), enc(g["items"]))
