@@ -52,6 +52,26 @@ class Coated:  # src/coat.rs:6-21: hides the tuple structure of I from Isomorphi
         return f"Coated<{self.inner!r}>"
 
 
+class Option:  # src/index.rs:244-276: None is position 0, Some(i) is 1 + i.to_usize()
+    def __init__(self, inner):
+        self.inner = inner
+
+    def __eq__(self, o):
+        return isinstance(o, Option) and o.inner == self.inner
+
+    def __hash__(self):
+        return hash(("Option", self.inner))
+
+    def __repr__(self):
+        return f"Option<{self.inner!r}>"
+
+
+class Some:
+    """Index VALUE `Some(i)` of an Option<I> axis (`None` is Python's None)."""
+    def __init__(self, i):
+        self.i = i
+
+
 class IndexError_(TypeError):
     """A constraint the Rust type checker would have rejected (e.g. a failed Isomorphic bound)."""
 
@@ -61,8 +81,8 @@ def is_tuple_type(I):
 
 
 def check_type(I):
-    if I is usize or I is Reversed or I is bool or isinstance(I, (Fixed, Coated)):
-        if isinstance(I, Coated):
+    if I is usize or I is Reversed or I is bool or isinstance(I, (Fixed, Coated, Option)):
+        if isinstance(I, (Coated, Option)):
             check_type(I.inner)
         return
     if isinstance(I, tuple):
@@ -105,6 +125,8 @@ def leaf_lengths(I, size):
         for t, s in zip(type_leaves(I.inner), size_leaves(I.inner, size)):
             out.extend(leaf_lengths(t, s))
         return out
+    if isinstance(I, Option):  # one position axis: [None, Some(0), Some(1), ...] (src/index.rs:248)
+        return [1 + length(I.inner, size)]
     raise IndexError_(f"not a leaf index type: {I!r}")
 
 
@@ -166,8 +188,8 @@ def coerce_size(I, size):
                 leaves.append(next(it))
             except StopIteration:
                 raise IndexError_(f"size {size!r} does not fit index type {I!r}")
-        elif isinstance(t, Coated):
-            raise IndexError_("give Coated sizes in full")
+        elif isinstance(t, (Coated, Option)):
+            raise IndexError_("give Coated / Option sizes in full")
         else:
             leaves.append(())
     if any(True for _ in it):
@@ -204,4 +226,13 @@ def index_positions(I, index, size):
         return [int(index)]
     if isinstance(I, Coated):
         return index_positions(I.inner, index, size)
+    if isinstance(I, Option):  # src/index.rs:250-256
+        if index is None:
+            return [0]
+        k = 0
+        inner = index.i if isinstance(index, Some) else index
+        lens = [n for t, s in zip(type_leaves(I.inner), size_leaves(I.inner, size)) for n in leaf_lengths(t, s)]
+        for p, n in zip(index_positions(I.inner, inner, size), lens):
+            k = k * n + p
+        return [1 + k]
     raise IndexError_(f"not an index type: {I!r}")

@@ -14,7 +14,7 @@ from . import _ffi as F
 from . import index as X
 from . import lowering as L
 from . import ops as O
-from .index import usize, Reversed, Fixed, Coated
+from .index import usize, Reversed, Fixed, Coated, Option
 from .runtime import Storage, default_context, NP_OF
 
 Panic = F.Panic
@@ -473,8 +473,8 @@ def _iota_value(I, groups):
         if isinstance(t, tuple):
             return tuple(build(x) for x in t)
         g = next(it)
-        if isinstance(t, Coated):
-            raise Unsupported("All<Coated<I>> elements have no device representation")
+        if isinstance(t, (Coated, Option)):
+            raise Unsupported(f"All<{t!r}> elements have no device representation")
         (a,) = g
         if t is Reversed:  # src/int.rs:82-84: position p holds Reversed(size-1-p)
             return L.Node(F.IOTA, F.U64, offset=a.length - 1, stride={a: -1})

@@ -206,3 +206,24 @@ def test_array_new_indexing(golden):  # src/array.rs:18-27
 def test_each_total(golden, run):  # src/view.rs:243-249: each() visits every element once, in order
     total = run(P.fold_rows(all_(usize, 5).map(lambda x: x + 0).iso(((), usize)), (), usize, P.Add, 0))
     assert as_list(total) == [golden["each_total"]["expect"]]
+
+
+def test_remaining_leaf_index_kinds(run):  # Reversed, Fixed<N>, bool, Option<I> (src/int.rs:33-86, src/index.rs:236-276)
+    from multidimension_b200 import Reversed, Fixed, Option, Some
+    from oracle import reference_model as R
+    items = list(range(100, 112))
+    a = Array.new((Option(usize), Fixed(3)), (3, ()), items)          # Option<usize> of size 3 has 1 + 3 positions
+    assert a.len() == 12 and a.size() == (3, ())
+    ra = R.Array.new((R.Option(R.usize), R.Fixed(3)), (3, ()), items)  # the pinned reference model agrees on every position
+    for i, ri in ((None, None), (Some(0), R.Some(0)), (Some(2), R.Some(2))):
+        for j in range(3):
+            assert a[(i, j)] == ra[(ri, j)]
+    t = a.transpose((), Fixed(3), Option(usize), ())
+    assert as_list(run(t)) == [items[p * 3 + f] for f in range(3) for p in range(4)]
+    assert as_list(run(a.row(Option(usize), Fixed(3), Some(1)))) == items[6:9]
+    assert as_list(run(a.column(Option(usize), Fixed(3), 2))) == items[2::3]
+    r = all_(Reversed, 4)                                              # position p holds Reversed(size-1-p), src/int.rs:82-84
+    assert as_list(run(r)) == [3, 2, 1, 0]
+    b = Array.new((bool, Reversed), ((), 3), [1, 2, 3, 4, 5, 6])
+    assert b[(True, 0)] == 6 and b[(False, 2)] == 1                   # Reversed(i).to_usize(size) = size-1-i, src/int.rs:74
+    assert as_list(run(b.row(bool, Reversed, True))) == [4, 5, 6]
