@@ -115,7 +115,7 @@ struct mdim_ctx {
     int eval_waves = 0;  // 0 = one trip per thread (non-persistent)
     int tr_ctas_per_sm = 0;
     uint64_t pos_base = 0;  // applied to collects issued while a host collect is chunking
-    size_t host_chunk_bytes = 32u << 20;
+    size_t host_chunk_bytes = 128u << 20;  // measured: 8 MB 60.7, 32 MB 73.1, 128 MB 75.8, 512 MB 76.3 GB/s end to end
 };
 
 namespace {
@@ -288,7 +288,7 @@ int mdim_init(int device, mdim_ctx** out) {
     ctx->eval_ctas_per_sm = env_int("MDIM_EVAL_CTAS_PER_SM", 8);
     ctx->eval_waves = env_int("MDIM_EVAL_WAVES", 0);
     ctx->tr_ctas_per_sm = env_int("MDIM_TR_CTAS_PER_SM", 0);
-    ctx->host_chunk_bytes = (size_t)std::max(1, env_int("MDIM_HOST_CHUNK_MB", 32)) << 20;
+    ctx->host_chunk_bytes = (size_t)std::max(1, env_int("MDIM_HOST_CHUNK_MB", 128)) << 20;
     bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&ctx->d_err, sizeof(ErrWord) * kErrSlots) == cudaSuccess &&
               cudaMallocHost(&ctx->h_err, sizeof(ErrWord) * kErrSlots) == cudaSuccess;
