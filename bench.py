@@ -383,9 +383,11 @@ def bench_ops(ctx, torch, ta, tout, dev_array, out_storage, time_launches, peak,
     assert torch.equal(dsts[0].view(n1, n1), srcs[0].view(n1, n1).t()), "transpose mismatch"
     state = {"k": 0}
 
+    prepared = [views[k].prepare(out=outs[k], flags=F.COLLECT_ASYNC) for k in range(R)]  # lowered once: a 20 us kernel must not wait for Python
+
     def tr():
         k = state["k"] = (state["k"] + 1) % R
-        views[k].collect(out=outs[k], flags=F.COLLECT_ASYNC)
+        prepared[k].run()
     ms, _ = time_launches(tr, steps * R, R)
     line("c1_transpose_4096x4096_f32", 2 * 4 * n1 * n1, ms, views[0].describe(), l2="16 rotating buffer pairs (2 GiB total)")
 

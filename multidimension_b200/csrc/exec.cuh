@@ -417,14 +417,21 @@ MDIM_FN uint32_t eval_preds(const Program& P, const ThreadState<WIDE, MAXR>& ts,
 #pragma unroll
         for (int a = 0; a < MAXR; ++a) s += (off_t)ts.c[a] * (off_t)P.pred[p].coef[a];
         const off_t rhs = (off_t)P.pred[p].rhs, lc = (off_t)P.pred[p].lane_coef;
-        const int cmp = P.pred[p].cmp;  // 0: ==   1: <   2: >=
+        // cmp 0: ==   1: <   2: >=   — evaluated with plain integer logic: a (uniform) branch per predicate
+        // here keeps the compiler from hoisting the operand loads that follow, which cost config 5 17 %.
+        const uint32_t is_eq = (uint32_t)(P.pred[p].cmp == 0), want_neg = (uint32_t)(P.pred[p].cmp == 1);
         if (lc == 0) {  // the vector axis is not involved: one test for all lanes
-            if (!(cmp == 0 ? s == rhs : cmp == 1 ? s < rhs : s >= rhs)) m = 0;
+            const off_t d = s - rhs;
+            const uint32_t zero = (uint32_t)(d == 0), neg = (uint32_t)(d < 0);
+            const uint32_t ok = (is_eq & zero) | ((1u ^ is_eq) & (1u ^ neg ^ want_neg));
+            m &= 0u - ok;
         } else {
 #pragma unroll
             for (int l = 0; l < V; ++l) {
-                const off_t x = s + (off_t)l * lc;
-                if (!(cmp == 0 ? x == rhs : cmp == 1 ? x < rhs : x >= rhs)) m &= ~(1u << l);
+                const off_t d = s + (off_t)l * lc - rhs;
+                const uint32_t zero = (uint32_t)(d == 0), neg = (uint32_t)(d < 0);
+                const uint32_t ok = (is_eq & zero) | ((1u ^ is_eq) & (1u ^ neg ^ want_neg));
+                m &= ~((1u ^ ok) << l);
             }
         }
     }
@@ -454,11 +461,11 @@ MDIM_FN int depth_delta(int opc, int aux) {
 // usize::to_usize (src/int.rs:16-19) in component order; inactive (off-diagonal) lanes neither
 // load nor report, because Diagonal::at never evaluates its inner view there (src/view.rs:854-856).
 template <int D, int NC, class S, int V, int MAXD, bool WIDE, int MAXR>
-MDIM_FN void exec_gather(const Program& P, ErrWord* err, const Instr& I, S (&st)[MAXD][V], const ThreadState<WIDE, MAXR>& ts) {
+MDIM_FN void exec_gather(const Program& P, ErrWord* err, const Instr& I, int slot, S (&st)[MAXD][V], const ThreadState<WIDE, MAXR>& ts) {
     if constexpr (sizeof(S) == 8 && D >= NC && NC >= 1) {
-        const Addr& A = P.addr[I.slot];
-        const int64_t base = (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts);
-        const int64_t s_in = inner_stride(P, I.slot);
+        const Addr& A = P.addr[slot];
+        const int64_t base = (int64_t)addr_offset<WIDE, MAXR>(P, slot, ts);
+        const int64_t s_in = inner_stride(P, slot);
         const int es = esize_of(I.dtype);
 #pragma unroll
         for (int l = 0; l < V; ++l) {
@@ -505,43 +512,47 @@ template <bool WIDE, int MAXR> MDIM_FN void advance_red(const Program& P, Thread
 }
 
 // Execute instruction I at compile-time stack depth D.  Returns the next pc.
-template <int D, class S, int V, int MAXD, bool WIDE, int MAXR>
+// SLOTK >= 0: the address slot is known at compile time (static signatures: slots are handed out in
+// instruction order, so it is the number of addressed instructions before this one).  Reading it from the
+// program instead makes every stride a register-indexed constant load (LDC) rather than a uniform one.
+template <int D, class S, int V, int MAXD, bool WIDE, int MAXR, int SLOTK = -1>
 MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int op, int aux, int pc,
                        S (&st)[MAXD][V], ThreadState<WIDE, MAXR>& ts) {
     const Instr& I = P.instr[pc];
+    const int slot = SLOTK >= 0 ? SLOTK : (int)I.slot;  // (address slot; MASK / SELECT read I.slot themselves)
     int next = pc + 1;
     switch (opc) {
         case OPC_LEAF_VEC:  // Array::at = items[to_usize(index)] (src/array.rs:81,86), V at a time
             if constexpr (D < MAXD) {
-                const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts);
+                const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, slot, ts);
                 if (ts.mask == (1u << V) - 1u) {  // (a compile-time fact in signatures without MASK)
-                    if (aux) ld_vector<S, V, true>(P.addr[I.slot].ptr, off, esize_of(dtype), st[D]);   // re-read operand: keep in L1
-                    else ld_vector<S, V, false>(P.addr[I.slot].ptr, off, esize_of(dtype), st[D]);      // read once: stream past L1
+                    if (aux) ld_vector<S, V, true>(P.addr[slot].ptr, off, esize_of(dtype), st[D]);   // re-read operand: keep in L1
+                    else ld_vector<S, V, false>(P.addr[slot].ptr, off, esize_of(dtype), st[D]);      // read once: stream past L1
                 } else {  // under a Concat / lazy Diagonal: inactive lanes must not touch memory
                     const int es = esize_of(dtype);
 #pragma unroll
-                    for (int l = 0; l < V; ++l) st[D][l] = ((ts.mask >> l) & 1u) ? ld_scalar<S>(P.addr[I.slot].ptr, off + l, es) : (S)0;
+                    for (int l = 0; l < V; ++l) st[D][l] = ((ts.mask >> l) & 1u) ? ld_scalar<S>(P.addr[slot].ptr, off + l, es) : (S)0;
                 }
             }
             break;
         case OPC_LEAF_BCAST:  // operand lacks the vector axis: Broadcast::index drops it (src/broadcast.rs:46-60)
             if constexpr (D < MAXD) {
-                const S v = ts.mask ? ld_scalar<S>(P.addr[I.slot].ptr, (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts), esize_of(dtype)) : (S)0;
+                const S v = ts.mask ? ld_scalar<S>(P.addr[slot].ptr, (int64_t)addr_offset<WIDE, MAXR>(P, slot, ts), esize_of(dtype)) : (S)0;
 #pragma unroll
                 for (int l = 0; l < V; ++l) st[D][l] = v;
             }
             break;
         case OPC_LEAF_STRIDED:
             if constexpr (D < MAXD) {
-                const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts), s_in = inner_stride(P, I.slot);
+                const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, slot, ts), s_in = inner_stride(P, slot);
                 const int es = esize_of(dtype);
 #pragma unroll
-                for (int l = 0; l < V; ++l) st[D][l] = ((ts.mask >> l) & 1u) ? ld_scalar<S>(P.addr[I.slot].ptr, off + (int64_t)l * s_in, es) : (S)0;
+                for (int l = 0; l < V; ++l) st[D][l] = ((ts.mask >> l) & 1u) ? ld_scalar<S>(P.addr[slot].ptr, off + (int64_t)l * s_in, es) : (S)0;
             }
             break;
         case OPC_IOTA:  // All<I>::at(index) = index (src/index.rs:185)
             if constexpr (D < MAXD) {
-                const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, I.slot, ts), s_in = inner_stride(P, I.slot);
+                const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, slot, ts), s_in = inner_stride(P, slot);
 #pragma unroll
                 for (int l = 0; l < V; ++l) {
                     const uint64_t x = (uint64_t)(off + (int64_t)l * s_in);
@@ -590,9 +601,9 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
             }
             break;
         case OPC_GATHER:
-            if (aux == 1) exec_gather<D, 1, S, V, MAXD, WIDE, MAXR>(P, err, I, st, ts);
-            else if (aux == 2) exec_gather<D, 2, S, V, MAXD, WIDE, MAXR>(P, err, I, st, ts);
-            else if (aux == 3) exec_gather<D, 3, S, V, MAXD, WIDE, MAXR>(P, err, I, st, ts);
+            if (aux == 1) exec_gather<D, 1, S, V, MAXD, WIDE, MAXR>(P, err, I, slot, st, ts);
+            else if (aux == 2) exec_gather<D, 2, S, V, MAXD, WIDE, MAXR>(P, err, I, slot, st, ts);
+            else if (aux == 3) exec_gather<D, 3, S, V, MAXD, WIDE, MAXR>(P, err, I, slot, st, ts);
             break;
         case OPC_FOLD_BEGIN:  // let mut s = init;  (the closure of rows().map(..))
             if constexpr (D < MAXD) {
@@ -637,6 +648,16 @@ template <class Sig> MDIM_CE int sig_fold_end(int pc) {
         if (Sig::code[i].opc == OPC_FOLD_STEP) return i;
     return Sig::n;
 }
+MDIM_CE bool sig_is_addressed(SigInstr I) {
+    return I.opc == OPC_LEAF_VEC || I.opc == OPC_LEAF_BCAST || I.opc == OPC_LEAF_STRIDED || I.opc == OPC_IOTA || I.opc == OPC_GATHER;
+}
+// address slot of instruction `pc`: plan.cpp hands slots out in instruction order
+template <class Sig> MDIM_CE int sig_addr_slot(int pc) {
+    int k = 0;
+    for (int i = 0; i < pc; ++i)
+        if (sig_is_addressed(Sig::code[i])) ++k;
+    return sig_is_addressed(Sig::code[pc]) ? k : -1;
+}
 MDIM_CE int sig_depth_after(SigInstr I, int d) {
     return d + (I.opc == OPC_LEAF_VEC || I.opc == OPC_LEAF_BCAST || I.opc == OPC_LEAF_STRIDED || I.opc == OPC_IOTA || I.opc == OPC_CONST ||
                         I.opc == OPC_FOLD_BEGIN ? 1
@@ -678,7 +699,7 @@ MDIM_FN void run_static(const Program& P, ErrWord* err, S (&st)[MAXD][V], Thread
             }
             run_static<Sig, END + 1, D + 1, STOP, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
         } else {
-            exec_instr<D, S, V, MAXD, WIDE, MAXR>(P, err, I.opc, I.dtype, I.op, I.aux, PC, st, ts);
+            exec_instr<D, S, V, MAXD, WIDE, MAXR, sig_addr_slot<Sig>(PC)>(P, err, I.opc, I.dtype, I.op, I.aux, PC, st, ts);
             run_static<Sig, PC + 1, sig_depth_after(I, D), STOP, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
         }
     }

@@ -227,6 +227,26 @@ class View:
         st = _build_like(self.T, list(storages)) if isinstance(self.T, tuple) else storages[0]
         return Array(I_out, size_out, st, self.T)
 
+    def prepare(self, out=None, ctx=None, flags=0):
+        """Lower once, run many times: returns a `Prepared` whose `run()` is a single C-ABI call (the lowering
+        and descriptor emission are not repeated).  Device-resident operands and scalar element types only."""
+        groups, value = self._lower()
+        if isinstance(value, tuple):
+            raise Unsupported("prepare() of a tuple-typed view: prepare the components")
+        ctx = ctx or default_context()
+
+        def visit(n):
+            for c in n.children:
+                visit(c)
+            if n.kind in (F.LEAF, F.GATHER) and n.buf is not None:
+                n.buf.ensure_device(ctx)
+        visit(value)
+        em = L.emit(value, _flat(groups), "device")
+        st = out if out is not None else Storage.device(ctx, em.out_dtype, em.out_len)
+        if st.n != em.out_len or st.dtype != em.out_dtype:
+            raise Panic(F.ERR_SIZE, "output buffer does not match the view")
+        return Prepared(ctx, em, st, Array(self.I, self._size, st, self.T), flags)
+
     def describe(self, flags=0):
         """Which kernel the planner picks for this chain (needs the library, not a GPU)."""
         from .runtime import describe_nodevice
@@ -307,6 +327,23 @@ class View:
     def __xor__(self, o): return self.binary(_as_view(o, self), O.BitXor)
     def __lshift__(self, o): return self.binary(_as_view(o, self), O.Shl)
     def __rshift__(self, o): return self.binary(_as_view(o, self), O.Shr)
+
+
+class Prepared:
+    """A lowered View chain bound to its operands and output buffer."""
+
+    def __init__(self, ctx, em, storage, array, flags):
+        import ctypes
+        self.ctx, self.em, self.storage, self.array, self.flags = ctx, em, storage, array, flags
+        self._collect = ctx.lib.mdim_collect
+        self._args = (ctx.handle, ctypes.byref(em.expr), ctypes.c_void_p(storage.dptr))
+
+    def run(self, flags=None):
+        """View::collect into the bound buffer (one kernel launch); returns the result Array."""
+        st = self._collect(*self._args, self.flags if flags is None else flags)
+        if st != F.OK:
+            self.ctx.check(st)
+        return self.array
 
 
 def _as_view(o, like):

@@ -39,14 +39,17 @@ def run(name, view, o, alg_bytes):
     view.collect(out=o, flags=args.flags)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    prep = view.prepare(out=o, flags=args.flags | F.COLLECT_ASYNC)
+    t0 = time.perf_counter()
     for _ in range(args.reps):
-        view.collect(out=o, flags=args.flags | F.COLLECT_ASYNC)
+        prep.run()
+    host_us = (time.perf_counter() - t0) / max(args.reps, 1) * 1e6
     e1.record(stream)
     torch.cuda.synchronize()
     ctx.sync()
     if args.time:
         ms = e0.elapsed_time(e1) / args.reps
-        print(f"  {name}: {ms:.4f} ms  {alg_bytes / ms / 1e6:.1f} GB/s", flush=True)
+        print(f"  {name}: {ms:.4f} ms  {alg_bytes / ms / 1e6:.1f} GB/s  (host {host_us:.1f} us/launch)", flush=True)
 
 
 n = 1 << 30
