@@ -172,7 +172,9 @@ typedef struct mdim_ctx mdim_ctx;
 #define MDIM_COLLECT_ASYNC 1u      /* do not synchronise; errors surface at mdim_sync */
 #define MDIM_COLLECT_NO_FASTPATH 2u /* force the general rank-N evaluator (testing/benchmarks) */
 #define MDIM_COLLECT_NO_STATIC 4u   /* force the interpreted op-tree (testing/benchmarks) */
+#define MDIM_COLLECT_NO_JIT 8u      /* do not specialise unlisted op trees at run time (NVRTC) */
 
+#ifndef __CUDACC_RTC__ /* (the declarations below are host functions; NVRTC compiles this header too) */
 /* ---- context ---------------------------------------------------------------------------------- */
 int mdim_init(int device, mdim_ctx** ctx);
 int mdim_shutdown(mdim_ctx* ctx);
@@ -214,7 +216,12 @@ int mdim_ipc_export(mdim_ctx* ctx, void* dptr, uint8_t handle[MDIM_IPC_HANDLE_BY
 int mdim_ipc_open(mdim_ctx* ctx, const uint8_t handle[MDIM_IPC_HANDLE_BYTES], void** dptr);
 int mdim_ipc_close(mdim_ctx* ctx, void* dptr);
 
+/* Run-time specialisation (NVRTC) of `e`'s op tree, compile step only: needs no GPU.  0 = compiles for
+ * sm_100a; MDIM_ERR_UNSUPPORTED = NVRTC not installed or the plan has a pre-built kernel; `log` gets details. */
+int mdim_jit_check_nodevice(const mdim_expr* e, uint32_t flags, char* log, size_t log_len);
+
 int mdim_abi_version(void);
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ NEG, NOT, ABS, SQRT, CAST = range(5)
 # node kinds
 LEAF, IOTA, CONST, UNARY, BINARY, DIAG, GATHER, FOLD, CONCAT = range(9)
 
-COLLECT_ASYNC, COLLECT_NO_FASTPATH, COLLECT_NO_STATIC = 1, 2, 4
+COLLECT_ASYNC, COLLECT_NO_FASTPATH, COLLECT_NO_STATIC, COLLECT_NO_JIT = 1, 2, 4, 8
 IPC_HANDLE_BYTES = 64
 
 
@@ -87,6 +87,7 @@ SYMBOLS = [
     ("mdim_ipc_export", C.c_int, [_P, _P, C.POINTER(C.c_uint8)]),
     ("mdim_ipc_open", C.c_int, [_P, C.POINTER(C.c_uint8), _PP]),
     ("mdim_ipc_close", C.c_int, [_P, _P]),
+    ("mdim_jit_check_nodevice", C.c_int, [C.POINTER(Expr), C.c_uint32, C.c_char_p, C.c_size_t]),
     ("mdim_abi_version", C.c_int, []),
 ]
 

@@ -160,19 +160,28 @@ int launch_eval(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err, bool expl
     if (!v) return set_error(ctx, MDIM_ERR_UNSUPPORTED, "no evaluator instantiation for this expression");
     uint64_t g0 = 0, g1 = p.prog.n_vec;
     int grid;
+    // an op tree without a pre-built signature is specialised on first use (jit.cu); else the interpreter runs
+    void* jit = nullptr;
+    if (p.static_id < 0 && !(p.flags & (MDIM_COLLECT_NO_STATIC | MDIM_COLLECT_NO_JIT))) jit = jit_kernel_for(p);
+    Program q = p.prog;
     if (explain) {
-        Program q = p.prog;
         q.flags |= PF_EXPLAIN;
         q.explain_pos = explain_pos;
         g0 = explain_pos / ((uint64_t)p.vec * (uint64_t)p.vpt);
         g1 = g0 + 1;
-        v->fn<<<1, kEvalThreads, 0, ctx->stream>>>(q, out, err, g0, g1);
+        grid = 1;
     } else {
         const uint64_t blocks = (g1 + kEvalThreads - 1) / kEvalThreads;
         uint64_t cap = 0x7fffffffull;
         if (ctx->eval_waves > 0) cap = (uint64_t)ctx->sm_count * ctx->eval_ctas_per_sm * ctx->eval_waves;
         grid = (int)std::min<uint64_t>(blocks, cap);
-        v->fn<<<grid, kEvalThreads, 0, ctx->stream>>>(p.prog, out, err, g0, g1);
+    }
+    if (jit) {
+        unsigned long long a0 = g0, a1 = g1;
+        void* args[] = {(void*)&q, (void*)&out, (void*)&err, (void*)&a0, (void*)&a1};
+        CU(ctx, cudaLaunchKernel((const void*)jit, dim3((unsigned)grid), dim3(kEvalThreads), args, 0, ctx->stream));
+    } else {
+        v->fn<<<grid, kEvalThreads, 0, ctx->stream>>>(q, out, err, g0, g1);
     }
     ctx->launches++;
     CU(ctx, cudaGetLastError());
@@ -459,9 +468,21 @@ int mdim_plan_describe_nodevice(const mdim_expr* e, uint32_t flags, char* buf, s
     if (st) snprintf(buf, buf_len, "%s", why);
     else {
         const EvalVariant* v = (plan->kind == KK_GENERIC || plan->kind == KK_STREAM) ? select_variant(*plan, false) : nullptr;
-        if (v) snprintf(buf, buf_len, "%s [%s r%d]", plan->describe, v->name, v->maxr);
+        const bool may_jit = plan->static_id < 0 && !(flags & (MDIM_COLLECT_NO_STATIC | MDIM_COLLECT_NO_JIT));
+        if (v) snprintf(buf, buf_len, "%s [%s r%d%s]", plan->describe, v->name, v->maxr, may_jit ? ", specialised on first use" : "");
         else snprintf(buf, buf_len, "%s", plan->describe);
     }
+    delete plan;
+    return st;
+}
+
+int mdim_jit_check_nodevice(const mdim_expr* e, uint32_t flags, char* log, size_t log_len) {
+    Plan* plan = new (std::nothrow) Plan();
+    if (!plan) return MDIM_ERR_NOMEM;
+    char why[160];
+    int st = plan_expr(e, flags, plan, why, sizeof why);
+    if (st) { if (log && log_len) snprintf(log, log_len, "%s", why); delete plan; return st; }
+    st = jit_compile_check(*plan, log, log_len);
     delete plan;
     return st;
 }

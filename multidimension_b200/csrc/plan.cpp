@@ -629,6 +629,7 @@ int plan_expr(const mdim_expr* e, uint32_t flags, Plan* plan, char* why_buf, siz
     if (why_buf && why_len) why_buf[0] = 0;
     memset(plan, 0, sizeof *plan);
     plan->static_id = -1;
+    plan->flags = flags;
     int st = b->validate();
     if (st) { delete b; return st; }
     // zero-length output: Array::new_view pushes nothing (src/array.rs:106-113)

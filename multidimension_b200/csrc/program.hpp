@@ -156,6 +156,7 @@ struct FoldRowsPlan {
 
 struct Plan {
     int32_t kind;
+    uint32_t flags;      // the MDIM_COLLECT_* flags the plan was made with
     int32_t slot_bytes;  // 4 or 8: width of the value-stack slots
     int32_t vec;
     int32_t vpt;         // vectors per thread trip
@@ -173,11 +174,18 @@ struct Plan {
     char describe[192];
 };
 
+#ifndef __CUDACC_RTC__  // host-side declarations (this header is also compiled by NVRTC, see jit.cu)
 int plan_expr(const mdim_expr* e, uint32_t flags, Plan* plan, char* why, size_t why_len);
 int dtype_size(int dt);
 const char* status_string(int st);
 
 // Signature registry (defined with the kernels; the planner only needs lookup by bytes).
+// jit.cu: a kernel specialised at run time for the plan's op sequence, or nullptr (use the interpreter)
+void* jit_kernel_for(const Plan& p);
+
 int find_static_signature(const char* sig, int sig_len, int slot_bytes, int vec, int vpt, int need_maxr, int wide);
+// NVRTC half of jit_kernel_for alone (needs no GPU): 0 = the specialisation compiles for sm_100a
+int jit_compile_check(const Plan& p, char* log, size_t log_len);
+#endif
 
 }  // namespace mdim

@@ -65,3 +65,30 @@ def test_planner_picks_the_intended_kernels():
     assert "SigDiagMulAddCF32 r5" in v5.describe()
     # contiguous arrays of any rank and any Iso regrouping collapse to the rank-1 stream kernel
     assert "rank=1+0" in (c * c).describe() and "rank=1+0" in (c.iso(((usize, usize), usize)) * c.iso(((usize, usize), usize))).describe()
+
+
+def test_runtime_specialisation_compiles_without_a_gpu():
+    """Op trees without a pre-built signature are specialised with NVRTC on first use; the compile half
+    needs no device, so the CPU suite checks that the embedded evaluator source builds for sm_100a."""
+    from multidimension_b200 import lowering as L
+    from multidimension_b200.view import _flat
+    rng = np.random.default_rng(0)
+    a = Array.new((usize, usize), (37, 24), rng.integers(0, 1000, 37 * 24).astype(np.uint64))
+    b = Array.new(usize, 24, rng.integers(1, 9, 24).astype(np.uint64))
+    f = Array.new(usize, 64, rng.uniform(-1, 1, 64).astype(np.float32))
+    views = [(a % b.iso(((), usize))) ^ Scalar(5),                      # integer ops with a broadcast operand
+             a.transpose((), usize, usize, ()).map(P.Cast("f32")).map(P.Sqrt),
+             (a >> Scalar(3)).diagonal(7),                              # predicates
+             (f * f - f).map(P.Abs),
+             fold_rows(a, usize, usize, P.BitXor, 0),                   # a fold becomes a real loop
+             f.concat(f, (), ()),                                       # masked sides
+             b.compose(a.row(usize, usize, 3)) + Scalar(1)]             # gather
+    for v in views:
+        groups, value = v._lower()
+        em = L.emit(value, _flat(groups), "any")
+        log = C.create_string_buffer(8000)
+        st = F.lib().mdim_jit_check_nodevice(C.byref(em.expr), 0, log, 8000)
+        if st == F.ERR_UNSUPPORTED and b"NVRTC" in log.value:
+            pytest.skip("NVRTC is not installed")
+        assert "specialised on first use" in v.describe()
+        assert st == F.OK, log.value.decode()
