@@ -342,3 +342,38 @@ def test_collect_host_chunked():
         Array.new(usize, iv.size, iv).compose(src).collect(ctx=c2)
     assert e.value.info.position == 300000
     c2.close()
+
+
+# ---- 64-bit coordinates (arrays past 2^31 elements): checked on the device against torch --------------------
+@pytest.mark.gpu
+def test_wide_coordinates_past_2_31_elements():
+    import torch
+    from multidimension_b200.runtime import Storage
+    c = P.Context(0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    c.set_stream(stream.cuda_stream)
+    n = (1 << 31) + 1024                                   # u8 stream: offsets need 64 bits
+    ta = torch.randint(0, 255, (n,), device="cuda", dtype=torch.uint8)
+    to = torch.empty(n, device="cuda", dtype=torch.uint8)
+    a = Array.from_device(usize, n, ta.data_ptr(), "u8", ctx=c, keep=ta)
+    v = a + Scalar(3, "u8")
+    assert " wide" in v.describe()
+    v.collect(out=Storage.wrap_device(c, F.U8, n, to.data_ptr(), keep=to), ctx=c)
+    assert torch.equal(to, ta + 3)                          # wrapping u8 add, every element
+    del ta, to, a, v
+    rows, cols = 1 << 16, (1 << 15) + 8                     # rank 2, 2^31 + 2^19 f32 elements, broadcast row vector
+    tm = torch.empty(rows * cols, device="cuda", dtype=torch.float32).uniform_(-1, 1)
+    tr = torch.empty(cols, device="cuda", dtype=torch.float32).uniform_(-1, 1)
+    tout = torch.empty(rows * cols, device="cuda", dtype=torch.float32)
+    m = Array.from_device((usize, usize), (rows, cols), tm.data_ptr(), "f32", ctx=c, keep=tm)
+    r = Array.from_device(usize, cols, tr.data_ptr(), "f32", ctx=c, keep=tr)
+    w = m - r.iso(((), usize))
+    assert " wide" in w.describe()
+    w.collect(out=Storage.wrap_device(c, F.F32, rows * cols, tout.data_ptr(), keep=tout), ctx=c)
+    assert torch.equal(tout.view(rows, cols), tm.view(rows, cols) - tr)
+    t = m.transpose((), usize, usize, ())                   # the tile kernel keeps 64-bit offsets too
+    t.collect(out=Storage.wrap_device(c, F.F32, rows * cols, tout.data_ptr(), keep=tout), ctx=c)
+    assert torch.equal(tout.view(cols, rows), tm.view(rows, cols).t())
+    torch.cuda.synchronize()
+    c.close()
