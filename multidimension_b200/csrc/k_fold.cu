@@ -236,6 +236,100 @@ k_fold_rows(const __grid_constant__ FoldRowsPlan R, void* __restrict__ out_v, in
     }
 }
 
+
+// ---- register-resident form (row_len = 32 * L elements, L a power of two <= 32) ------------------------
+// No shared memory, no TMA, no barrier: the massively threaded, one-trip-per-warp shape that the plain
+// streaming kernels use.  L lanes share a row; lane j holds the 16-byte chunks j, L + j, 2L + j, ... (so every
+// load and store instruction of the warp covers whole 16L-byte runs of 32/L adjacent rows), and the fold is
+// passed around the L lanes in INDEX ORDER — chunk c is added by lane c % L, then the running value is
+// broadcast to the group by shuffle — so the add chain is exactly the reference's sequential one.
+// The row stays in registers for the fused epilogue: the input is read from HBM once.
+template <int L, bool FAST>
+__global__ void __launch_bounds__(256) k_fold_regs(const __grid_constant__ FoldRowsPlan R, void* __restrict__ out_v) {
+    constexpr int M = 8;         // 16-byte chunks per lane
+    constexpr int RPW = 32 / L;  // rows per warp
+    const int lane = threadIdx.x & 31, j = lane % L, grp = lane / L;
+    const uint64_t warp = (uint64_t)blockIdx.x * (256 / 32) + (threadIdx.x >> 5);
+    const uint64_t row = warp * RPW + grp;
+    const bool live = row < R.n_rows;
+    const uint64_t row_bytes = (uint64_t)R.row_len * 4u;
+    const char* __restrict__ src = (const char*)R.src + R.src_offset * 4 + row * row_bytes;
+    uint4 v[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        v[m] = make_uint4(0, 0, 0, 0);
+        if (live)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v[m].x), "=r"(v[m].y), "=r"(v[m].z), "=r"(v[m].w) : "l"(src + (size_t)(m * L + j) * 16u));
+    }
+    uint32_t acc = (uint32_t)R.init;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+#pragma unroll
+        for (int jj = 0; jj < L; ++jj) {
+            if (j == jj) {  // chunk m * L + jj: strictly after chunk m * L + jj - 1
+                if constexpr (FAST) {
+                    float a = __uint_as_float(acc);
+                    a = __fadd_rn(a, __uint_as_float(v[m].x));
+                    a = __fadd_rn(a, __uint_as_float(v[m].y));
+                    a = __fadd_rn(a, __uint_as_float(v[m].z));
+                    a = __fadd_rn(a, __uint_as_float(v[m].w));
+                    acc = __float_as_uint(a);
+                } else {
+                    acc = apply_any(R.dtype, R.op, acc, v[m].x);
+                    acc = apply_any(R.dtype, R.op, acc, v[m].y);
+                    acc = apply_any(R.dtype, R.op, acc, v[m].z);
+                    acc = apply_any(R.dtype, R.op, acc, v[m].w);
+                }
+            }
+            if constexpr (L > 1) acc = __shfl_sync(0xffffffffu, acc, grp * L + jj);
+        }
+    }
+    // every lane of the group now holds the row's fold
+    if (R.epilogue == 0) {
+        if (live && j == 0) reinterpret_cast<uint32_t*>(out_v)[row] = acc;
+        return;
+    }
+    uint32_t g = acc;
+    if (R.has_post) g = apply_any(R.dtype, R.post_op, g, (uint32_t)R.post_imm);
+    char* __restrict__ orow = (char*)out_v + row * row_bytes;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        uint4 x = v[m];
+        if constexpr (FAST) {
+            const float mm = __uint_as_float(g);
+            x.x = __float_as_uint(__fsub_rn(__uint_as_float(x.x), mm));
+            x.y = __float_as_uint(__fsub_rn(__uint_as_float(x.y), mm));
+            x.z = __float_as_uint(__fsub_rn(__uint_as_float(x.z), mm));
+            x.w = __float_as_uint(__fsub_rn(__uint_as_float(x.w), mm));
+        } else {
+            x.x = apply_any(R.dtype, R.eop, x.x, g);
+            x.y = apply_any(R.dtype, R.eop, x.y, g);
+            x.z = apply_any(R.dtype, R.eop, x.z, g);
+            x.w = apply_any(R.dtype, R.eop, x.w, g);
+        }
+        if (live) asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(orow + (size_t)(m * L + j) * 16u), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+    }
+}
+
+template <bool FAST> static bool launch_regs(const FoldRowsPlan& R, void* out, cudaStream_t stream) {
+    const uint32_t L = R.row_len / 32;  // row_len = 4 elements x 8 chunks x L lanes
+    if (R.row_len % 32 != 0 || L < 1 || L > 32 || (L & (L - 1)) != 0) return false;
+    const uint64_t warps = (R.n_rows + (32 / L) - 1) / (32 / L);
+    const uint64_t ctas = (warps + 7) / 8;
+    if (ctas > 0x7fffffffull) return false;
+    const dim3 grid((unsigned)ctas), block(256);
+    switch (L) {
+        case 1: k_fold_regs<1, FAST><<<grid, block, 0, stream>>>(R, out); break;
+        case 2: k_fold_regs<2, FAST><<<grid, block, 0, stream>>>(R, out); break;
+        case 4: k_fold_regs<4, FAST><<<grid, block, 0, stream>>>(R, out); break;
+        case 8: k_fold_regs<8, FAST><<<grid, block, 0, stream>>>(R, out); break;
+        case 16: k_fold_regs<16, FAST><<<grid, block, 0, stream>>>(R, out); break;
+        default: k_fold_regs<32, FAST><<<grid, block, 0, stream>>>(R, out); break;
+    }
+    return true;
+}
+
 }  // namespace
 
 void launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream_t stream) {
@@ -265,6 +359,11 @@ void launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream
     // bank-conflict-free skew needs the dense row pitch to be a multiple of 8 sixteen-byte chunks
     const int skew = ((ch / 4) % 8 == 0) ? 1 : 0;
     const bool fast = R.dtype == MDIM_F32 && R.op == MDIM_ADD && (R.epilogue == 0 || (R.eop == MDIM_SUB));
+    // Measured on B200 (profiles/): the register form wins for the fused epilogue (config 4c: 6.27 vs 5.74 TB/s),
+    // the TMA / shared-memory form for the fold alone (config 4a: 6.28 vs 5.66 TB/s).
+    static const int mode = [] { const char* e = getenv("MDIM_FOLD_MODE"); return e ? atoi(e) : 0; }();  // 1 = always smem, 2 = always registers
+    const bool want_regs = mode == 2 || (mode == 0 && R.epilogue != 0);
+    if (want_regs && (fast ? launch_regs<true>(R, out, stream) : launch_regs<false>(R, out, stream))) return;
     // i / q4 for the flat epilogue walk: umulhi(i, mul) >> shr, exact for i < 2^31 (q4 >= 2 here)
     uint32_t q4 = (uint32_t)ch / 4, lg = 0;
     while ((1u << lg) < q4) ++lg;
