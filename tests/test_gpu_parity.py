@@ -377,3 +377,34 @@ def test_wide_coordinates_past_2_31_elements():
     assert torch.equal(tout.view(cols, rows), tm.view(rows, cols).t())
     torch.cuda.synchronize()
     c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_both_fold_kernels_for_both_forms(mode):
+    """MDIM_FOLD_MODE forces the shared-memory/TMA form (1) or the register form (2) for fold-only AND fused
+    chains (by default each serves the form it is faster for); both must stay bit-exact and sequential."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests")
+from helpers import assert_same_bits
+import multidimension_b200 as P
+from multidimension_b200 import usize, Array, Scalar, Add, fold_rows
+ctx = P.Context(0); P.set_default_context(ctx)
+rng = np.random.default_rng(1)
+for rows, n in [(1, 32), (77, 64), (1000, 256), (33, 512), (130, 1024), (64, 96), (9, 2048)]:
+    x = rng.uniform(0, 1, rows * n).astype(np.float32)
+    a = Array.new((usize, usize), (rows, n), x)
+    s = fold_rows(a, usize, usize, Add, np.float32(0))
+    seq = np.add.accumulate(x.reshape(rows, n), axis=1, dtype=np.float32)[:, -1]
+    assert_same_bits(s.collect(location="device").as_ref(), seq, f"fold {rows}x{n}")
+    fused = a - (s / Scalar(float(n), "f32")).iso((usize, ()))
+    want = (x.reshape(rows, n) - (seq / np.float32(n))[:, None]).reshape(-1)
+    assert_same_bits(fused.collect(location="device").as_ref(), want, f"fused {rows}x{n}")
+print("ok")
+'''
+    env = dict(os.environ, MDIM_FOLD_MODE=mode)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
