@@ -505,6 +505,30 @@ def bench_multi_ops(ctx, torch, dist, rank, world, ta, tout, dev_array, out_stor
                                                "note": "ncclAllGather of the 4 GiB source + local gather"}
     peers.close()
     del full, full_buf, tidx
+    # (d) BASELINE config 5 — the rank-5 transpose -> diagonal -> broadcast -> map chain, 2^30 outputs — sharded
+    #     over the ranks along its outermost index (strong scaling: every rank writes 2^30 / world elements)
+    Pn = Qn = Rn = 64
+    g5 = torch.Generator(device="cuda")
+    g5.manual_seed(0x5EED0005)  # the same small operands on every rank (replicated)
+    ta5 = torch.empty(Pn * Qn, device="cuda", dtype=torch.float32).uniform_(-1, 1, generator=g5)
+    tw5 = torch.empty(Rn, device="cuda", dtype=torch.float32).uniform_(-1, 1, generator=g5)
+    v5 = (dev_array((usize, usize), (Pn, Qn), ta5, "f32").transpose((), usize, usize, ()).diagonal(np.float32(0))
+          .iso((((usize, usize), (usize, usize)), ())).zip(dev_array(usize, Rn, tw5, "f32").iso(((), usize))).map(lambda p: p[0] * p[1] + np.float32(1)))
+    mine = sharding.shard_view(v5, rank, world)
+    n5 = mine.len()
+    o5 = out_storage(tout[:n5], F.F32)
+    prep5 = mine.prepare(out=o5, flags=F.COLLECT_ASYNC)
+    prep5.run()
+    torch.cuda.synchronize()
+    q_lo, q_hi = sharding.shard_bounds(Qn, world, rank)
+    eye = torch.eye(Pn * Qn, device="cuda", dtype=torch.float32)[q_lo * Pn:q_hi * Pn]
+    want5 = (eye * ta5.view(Pn, Qn).t().reshape(-1).unsqueeze(0)).reshape(-1, 1) * tw5.view(1, Rn)
+    want5 += 1.0
+    assert torch.equal(tout[:n5].view(-1, Rn), want5), "sharded rank-5 chain mismatch"
+    del want5, eye
+    ms, _ = time_launches(prep5.run, 10, 3)
+    out["c5_rank5_chain_sharded_outermost"] = {"GB/s": round(4 * (1 << 30) / (ms * 1e-3) / 1e9, 1), "ms": round(ms, 4), "kernel": mine.describe(),
+                                               "note": f"BASELINE configs[4]: 2^30 outputs cut into {world} blocks of the outermost index, no collective (strong scaling)"}
     # (c) fold over the SHARDED (outermost) axis + all-reduce: a (1024,1024,256) f32 Array sharded on axis 0
     I, J, K = 1024 // world, 1024, 256
     t4 = ta[: I * J * K]

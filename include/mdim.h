@@ -136,7 +136,8 @@ typedef struct mdim_node {
     int64_t gstride[MDIM_MAX_RANK]; /* GATHER: elements per unit of index component c */
     uint64_t bound[MDIM_MAX_RANK];  /* GATHER: size of component c; idx >= bound is MDIM_ERR_OOB */
     int32_t axis_a[MDIM_MAX_RANK];  /* DIAG pair p: iteration axis on the left ... (CONCAT: [0] = the axis) */
-    int32_t axis_b[MDIM_MAX_RANK];  /* ... equals iteration axis on the right, or, if axis_b[p] < 0, */
+    int32_t axis_b[MDIM_MAX_RANK];  /* ... equals iteration axis on the right PLUS (int64_t)axis_c[p] (a shard of a
+                                       Diagonal: its block starts at a non-zero coordinate), or, if axis_b[p] < 0, */
     uint64_t axis_c[MDIM_MAX_RANK]; /* ... equals the constant axis_c[p] (a Row/Column of a Diagonal);
                                        CONCAT: [0] = length of V along the axis; W's strides are already
                                        expressed against the concatenated coordinate (offset shifted) */

@@ -332,7 +332,7 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
                 const int a = axis_map[n.axis_a[p]];
                 const int b = n.axis_b[p] >= 0 ? axis_map[n.axis_b[p]] : -1;
                 pr.coef[pa(a)] += 1;
-                if (b >= 0) pr.coef[pa(b)] -= 1;
+                if (b >= 0) { pr.coef[pa(b)] -= 1; pr.rhs = (int64_t)n.axis_c[p]; }  // coord[a] == coord[b] + offset
                 else if (n.axis_c[p] >= len[a]) { pr.coef[pa(a)] = 0; pr.rhs = 1; }  // never on the diagonal
                 else pr.rhs = (int64_t)n.axis_c[p];
                 pr.lane_coef = rank > 0 ? pr.coef[0] : 0;

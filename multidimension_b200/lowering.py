@@ -53,7 +53,7 @@ class Node:
         self.stride = kw.get("stride", {})  # {Axis: int}
         self.gstride = kw.get("gstride", ())
         self.bound = kw.get("bound", ())
-        self.pairs = kw.get("pairs", ())    # DIAG: ((Axis, Axis | int), ...)
+        self.pairs = kw.get("pairs", ())    # DIAG: ((Axis, Axis | int[, offset]), ...): coord[a] == coord[b] + offset | == int
         self.imm = kw.get("imm", 0)         # raw python value of `dtype`
         self.src_dtype = kw.get("src_dtype", 0)
         self.red_axes = kw.get("red_axes", ())  # FOLD: reduction axes, iterated last-fastest
@@ -119,17 +119,29 @@ def substitute(node, table, memo=None):
                 for n, coef in sub.terms:
                     stride[n] = stride.get(n, 0) + s * coef
         out = node.clone(stride={a: s for a, s in stride.items() if s != 0}, offset=offset, children=kids)
-    elif node.kind == F.DIAG and any((a in table) or (not isinstance(b, int) and b in table) for a, b in node.pairs):
+    elif node.kind == F.DIAG and any((pr[0] in table) or (not isinstance(pr[1], int) and pr[1] in table) for pr in node.pairs):
+        # each side is (axis | None, constant): coord[a] + ca == coord[b] + cb
         pairs, dead = [], False
-        for a, b in node.pairs:
-            a2, b2 = _sub_pred_side(a, table), _sub_pred_side(b, table)
-            if isinstance(a2, int) and isinstance(b2, int):
-                if a2 != b2:
+        for pr in node.pairs:
+            a, b = pr[0], pr[1]
+            off = pr[2] if len(pr) > 2 else 0
+            a2, ca = _sub_pred_side(a, table)
+            b2, cb = _sub_pred_side(b, table)
+            cb += off
+            if a2 is None and b2 is None:
+                if ca != cb:
                     dead = True  # statically off the diagonal
                 continue
-            if isinstance(a2, int):
-                a2, b2 = b2, a2
-            pairs.append((a2, b2))
+            if a2 is None:  # const == coord[b] + cb  ->  coord[b] == const - cb
+                a2, b2, ca, cb = b2, None, cb, ca
+            if b2 is None:
+                k = cb - ca
+                if k < 0:
+                    dead = True
+                    continue
+                pairs.append((a2, int(k)))
+            else:
+                pairs.append((a2, b2, cb - ca))
         if dead:
             out = Node(F.CONST, node.dtype, imm=node.imm)
         elif not pairs:
@@ -153,15 +165,16 @@ def substitute(node, table, memo=None):
 
 
 def _sub_pred_side(x, table):
+    """-> (axis | None, constant): the coordinate x after substitution is coord[axis] + constant."""
     if isinstance(x, int):
-        return x
+        return None, x
     sub = table.get(x)
     if sub is None:
-        return x
+        return x, 0
     if not sub.terms:
-        return int(sub.const)
-    if len(sub.terms) == 1 and sub.terms[0][1] == 1 and sub.const == 0:
-        return sub.terms[0][0]
+        return None, int(sub.const)
+    if len(sub.terms) == 1 and sub.terms[0][1] == 1:
+        return sub.terms[0][0], int(sub.const)
     raise Unsupported("a Diagonal whose axis has been split or merged needs device div/mod")
 
 
@@ -242,13 +255,15 @@ def emit(root, axes, location):
                 d.bound[c] = n.bound[c]
         if n.kind == F.DIAG:
             d.n_comp = len(n.pairs)
-            for p, (a, b) in enumerate(n.pairs):
+            for p, pr in enumerate(n.pairs):
+                a, b = pr[0], pr[1]
                 d.axis_a[p] = pos[a]
                 if isinstance(b, int):
                     d.axis_b[p] = -1
                     d.axis_c[p] = b
                 else:
                     d.axis_b[p] = pos[b]
+                    d.axis_c[p] = (pr[2] if len(pr) > 2 else 0) & 0xFFFFFFFFFFFFFFFF
             d.imm.u64 = imm_bits(n.dtype, n.imm)
         if n.kind == F.CONCAT:
             d.axis_a[0] = pos[n.pairs[0][0]]

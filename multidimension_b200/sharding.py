@@ -36,6 +36,42 @@ def equal_block(length, world):
     return -(-int(length) // int(world))
 
 
+def shard_view(view, rank, world):
+    """The block of `view` owned by `rank` when its OUTERMOST position axis is cut into `world` contiguous
+    blocks (the north star's partitioning): a View over the same index type whose outermost axis is shorter.
+    Pure lowering — the outer coordinate becomes lo + k — so the block is still one fused kernel."""
+    from . import lowering as L
+    from .view import View, _flat
+
+    class Shard(View):
+        def __init__(self):
+            groups, _ = view._lower()
+            axes = _flat(groups)
+            if not axes:
+                raise ValueError("a rank-0 view has no axis to shard")
+            self.lo, self.hi = shard_bounds(axes[0].length, world, rank)
+            leaves = X.size_leaves(view.I, view._size)
+            types = X.type_leaves(view.I)
+            first = next(i for i, (t, s) in enumerate(zip(types, leaves)) if X.leaf_lengths(t, s))
+            if len(X.leaf_lengths(types[first], leaves[first])) != 1 or types[first] not in (X.usize, X.Reversed):
+                raise ValueError("the outermost axis must be a usize axis to be sharded")
+            leaves = list(leaves)
+            leaves[first] = self.hi - self.lo
+            self.I, self.T = view.I, view.T
+            self._size = X.build_size(view.I, leaves)
+
+        def _lower(self):
+            groups, value = view._lower()
+            axes = _flat(groups)
+            k = L.Axis(self.hi - self.lo)
+            table = {axes[0]: L.Sub(self.lo, ((k, 1),))}
+            memo = {}
+            new_groups = [[k if a is axes[0] else a for a in g] for g in groups]
+            return new_groups, L.map_value(value, lambda n: L.substitute(n, table, memo))
+
+    return Shard()
+
+
 class PeerStorage(Storage):
     """A source Array split into `world` equal blocks of `block` elements, block p living on rank p.
     Only gathers (`compose`, `map_axis`) can read it; the kernel picks the peer per element."""

@@ -307,7 +307,7 @@ static mdim_scalar at(oracle_t* o, int ni) {
         case MDIM_NODE_DIAG: { /* src/view.rs:854-856: inner evaluated ONLY on the diagonal */
             for (int p = 0; p < n->n_comp; ++p) {
                 uint64_t lhs = o->coord[n->axis_a[p]];
-                uint64_t rhs = n->axis_b[p] >= 0 ? o->coord[n->axis_b[p]] : n->axis_c[p];
+                uint64_t rhs = n->axis_b[p] >= 0 ? o->coord[n->axis_b[p]] + n->axis_c[p] /* wrapping: signed offset */ : n->axis_c[p];
                 if (lhs != rhs) return n->imm;
             }
             return at(o, o->child[ni][0]);

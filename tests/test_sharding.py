@@ -65,6 +65,41 @@ def test_peer_sharded_compose_gpu():
     ctx.close()
 
 
+def _shardable_views(rng):
+    a = Array.new((usize, usize), (3, 5), rng.uniform(-1, 1, 15).astype(np.float32))
+    w = Array.new(usize, 8, rng.uniform(-1, 1, 8).astype(np.float32))
+    m = Array.new((usize, usize), (7, 6), rng.uniform(-1, 1, 42).astype(np.float32))
+    idx = Array.new(usize, 11, rng.integers(0, 42, 11).astype(np.uint64))
+    c5 = (a.transpose((), usize, usize, ()).diagonal(np.float32(0)).iso((((usize, usize), (usize, usize)), ()))
+          .zip(w.iso(((), usize))).map(lambda p: p[0] * p[1] + np.float32(1)))                 # BASELINE config 5
+    return [c5, m.transpose((), usize, usize, ()), m * m + Scalar(1.0, "f32"), P.all_(usize, 6).map(lambda x: x + 10).diagonal(0),
+            idx.compose(Array.new(usize, 42, rng.uniform(-1, 1, 42).astype(np.float32))), fold_rows(m, usize, usize, Add, np.float32(0)),
+            m.concat(m, (), usize)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shard_view_blocks_tile_the_full_result(world):
+    """`shard_view(v, rank, world)` is the block of v along its outermost index; the blocks of all ranks,
+    concatenated, are the unsharded collect — including under a diagonal (the shard's predicate gets an offset)."""
+    from multidimension_b200.sharding import shard_view
+    for v in _shardable_views(np.random.default_rng(world)):
+        full = oracle_collect(v)
+        for run in (oracle_collect, emu_collect):
+            parts = [run(shard_view(v, r, world)) for r in range(world)]
+            assert_same_bits(np.concatenate(parts), full, f"{v.describe()} x{world}")
+
+
+@pytest.mark.gpu
+def test_shard_view_gpu():
+    from multidimension_b200.sharding import shard_view
+    ctx = P.Context(0)
+    for v in _shardable_views(np.random.default_rng(4)):
+        full = oracle_collect(v)
+        parts = [shard_view(v, r, 4).collect(location="device", ctx=ctx).as_ref() for r in range(4)]
+        assert_same_bits(np.concatenate(parts), full, str(v.describe()))
+    ctx.close()
+
+
 # ---- world_size-2 gloo: the per-rank flow of bench.py / a sharded application ---------------------------
 def _free_port():
     s = socket.socket()
