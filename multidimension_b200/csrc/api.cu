@@ -162,8 +162,10 @@ int launch_eval(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err, bool expl
     int grid;
     // an op tree without a pre-built signature is specialised on first use (jit.cu); else the interpreter runs
     void* jit = nullptr;
-    if (p.static_id < 0 && !(p.flags & (MDIM_COLLECT_NO_STATIC | MDIM_COLLECT_NO_JIT))) jit = jit_kernel_for(p);
+    if (!(p.flags & (MDIM_COLLECT_NO_STATIC | MDIM_COLLECT_NO_JIT))) jit = jit_kernel_for(p);
     Program q = p.prog;
+    static const bool no256 = [] { const char* e = getenv("MDIM_NO_VEC256"); return e && e[0] == '1'; }();
+    if (p.vec256_ok && !no256 && ((uintptr_t)out % 32) == 0) q.flags |= PF_VEC256;
     if (explain) {
         q.flags |= PF_EXPLAIN;
         q.explain_pos = explain_pos;

@@ -28,6 +28,18 @@
 #define MDIM_CE constexpr
 #endif
 
+// SHAPE-LIKE fields of the program (ranks, lengths, strides, dividers, predicate forms, opcodes' slot
+// numbers) are read through MDIM_SHAPE_OF(P).  Normally that is the run-time program itself; the run-time
+// specialiser (jit.cu) can instead point it at a `constexpr Program` generated for one concrete shape, which
+// turns every stride into an immediate, drops zero strides and length-1 axes, and makes every divider a
+// compile-time constant.  Pointers, offsets and immediates always come from the real program.
+#ifndef MDIM_STORE_STREAMING
+#define MDIM_STORE_STREAMING true  // st.global.cs (evict-first): nothing re-reads the output
+#endif
+#ifndef MDIM_SHAPE_OF
+#define MDIM_SHAPE_OF(P) (P)
+#endif
+
 namespace mdim {
 
 // ------------------------------------------------------------------------------------------------
@@ -73,6 +85,22 @@ MDIM_FN void ld128_stream(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, 
 MDIM_FN void ld128_cached(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
 }
+// 256-bit accesses (new on sm_100): one instruction moves a thread's whole 32-byte vector, so a warp
+// instruction covers 1 KB of whole sectors.  With two 128-bit accesses per thread every instruction touches
+// HALF of each 32-byte sector: harmless for reads, but a write-only stream then runs at 4.0 instead of
+// 7.6 TB/s (profiles/: iota collect), and the write-bound rank-5 chain at 4.2 instead of 6.4.
+MDIM_FN void ld256_stream(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+MDIM_FN void ld256_cached(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+MDIM_FN void st256(void* p, const uint32_t (&r)[8], bool cs) {
+    if (cs) asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+    else asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 MDIM_FN void ld64_stream(const void* p, uint32_t& a, uint32_t& b) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
 }
@@ -97,6 +125,9 @@ MDIM_FN void ld128_stream(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, 
     const uint32_t* q = (const uint32_t*)p; a = q[0]; b = q[1]; c = q[2]; d = q[3];
 }
 MDIM_FN void ld128_cached(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) { ld128_stream(p, a, b, c, d); }
+MDIM_FN void ld256_stream(const void* p, uint32_t (&r)[8]) { memcpy(r, p, 32); }
+MDIM_FN void ld256_cached(const void* p, uint32_t (&r)[8]) { memcpy(r, p, 32); }
+MDIM_FN void st256(void* p, const uint32_t (&r)[8], bool) { memcpy(p, r, 32); }
 MDIM_FN void ld64_stream(const void* p, uint32_t& a, uint32_t& b) { const uint32_t* q = (const uint32_t*)p; a = q[0]; b = q[1]; }
 MDIM_FN uint32_t ld32_stream(const void* p) { return *(const uint32_t*)p; }
 MDIM_FN uint32_t ld32(const void* p) { return *(const uint32_t*)p; }
@@ -121,7 +152,21 @@ template <class S> MDIM_FN S ld_scalar(const void* base, int64_t idx, int esize)
 }
 
 // V consecutive elements starting at element `idx`; the planner guarantees the alignment.
-template <class S, int V, bool CACHED> MDIM_FN void ld_vector(const void* base, int64_t idx, int esize, S (&d)[V]) {
+template <class S, int V, bool CACHED> MDIM_FN void ld_vector(const void* base, int64_t idx, int esize, S (&d)[V], bool w256 = false) {
+    if constexpr (V * sizeof(S) == 32 && (sizeof(S) == 4 || sizeof(S) == 8)) {
+        if (w256 && esize == (int)sizeof(S)) {  // the whole 32-byte vector in one access
+            uint32_t r[8];
+            if constexpr (CACHED) ld256_cached((const char*)base + idx * esize, r); else ld256_stream((const char*)base + idx * esize, r);
+            if constexpr (sizeof(S) == 4) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] = (S)r[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[i] = (S)r[2 * i] | ((S)r[2 * i + 1] << 32);
+            }
+            return;
+        }
+    }
     if (esize == 4) {
         const char* p = (const char*)base + idx * 4;
         if constexpr (V % 4 == 0) {
@@ -167,7 +212,21 @@ template <class S, int V, bool CACHED> MDIM_FN void ld_vector(const void* base, 
     }
 }
 
-template <class S, int V> MDIM_FN void st_vector(void* base, uint64_t idx, int esize, const S (&d)[V], bool cs) {
+template <class S, int V> MDIM_FN void st_vector(void* base, uint64_t idx, int esize, const S (&d)[V], bool cs, bool w256 = false) {
+    if constexpr (V * sizeof(S) == 32 && (sizeof(S) == 4 || sizeof(S) == 8)) {
+        if (w256 && esize == (int)sizeof(S)) {
+            uint32_t r[8];
+            if constexpr (sizeof(S) == 4) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = (uint32_t)d[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { r[2 * i] = (uint32_t)d[i]; r[2 * i + 1] = (uint32_t)((uint64_t)d[i] >> 32); }
+            }
+            st256((char*)base + idx * esize, r, cs);
+            return;
+        }
+    }
     if (esize == 4) {
         char* p = (char*)base + idx * 4;
         if constexpr (V % 4 == 0) {
@@ -398,13 +457,13 @@ template <bool WIDE, int MAXR> struct ThreadState {
 template <bool WIDE, int MAXR>
 MDIM_FN typename CoordTraits<WIDE>::off_t addr_offset(const Program& P, int slot, const ThreadState<WIDE, MAXR>& ts) {
     using off_t = typename CoordTraits<WIDE>::off_t;
-    off_t off = (off_t)P.addr[slot].offset + (off_t)ts.rk * (off_t)P.addr[slot].rstride;
+    off_t off = (off_t)P.addr[slot].offset + (off_t)ts.rk * (off_t)MDIM_SHAPE_OF(P).addr[slot].rstride;
 #pragma unroll
-    for (int a = 0; a < MAXR; ++a) off += (off_t)ts.c[a] * (off_t)P.addr[slot].stride[a];
+    for (int a = 0; a < MAXR; ++a) off += (off_t)ts.c[a] * (off_t)MDIM_SHAPE_OF(P).addr[slot].stride[a];
     return off;
 }
 
-MDIM_FN int64_t inner_stride(const Program& P, int slot) { return P.addr[slot].inner; }
+MDIM_FN int64_t inner_stride(const Program& P, int slot) { (void)P; return MDIM_SHAPE_OF(P).addr[slot].inner; }
 
 // Predicates are linear forms: sum_a coef[a] * coord[a] (+ lane * lane_coef) == rhs.
 // `coord[a] == coord[b]` is coef[a] = 1, coef[b] = -1, rhs = 0; `coord[a] == k` is coef[a] = 1, rhs = k.
@@ -415,11 +474,11 @@ MDIM_FN uint32_t eval_preds(const Program& P, const ThreadState<WIDE, MAXR>& ts,
     for (int p = first; p < first + n; ++p) {
         off_t s = 0;
 #pragma unroll
-        for (int a = 0; a < MAXR; ++a) s += (off_t)ts.c[a] * (off_t)P.pred[p].coef[a];
-        const off_t rhs = (off_t)P.pred[p].rhs, lc = (off_t)P.pred[p].lane_coef;
+        for (int a = 0; a < MAXR; ++a) s += (off_t)ts.c[a] * (off_t)MDIM_SHAPE_OF(P).pred[p].coef[a];
+        const off_t rhs = (off_t)MDIM_SHAPE_OF(P).pred[p].rhs, lc = (off_t)MDIM_SHAPE_OF(P).pred[p].lane_coef;
         // cmp 0: ==   1: <   2: >=   — evaluated with plain integer logic: a (uniform) branch per predicate
         // here keeps the compiler from hoisting the operand loads that follow, which cost config 5 17 %.
-        const uint32_t is_eq = (uint32_t)(P.pred[p].cmp == 0), want_neg = (uint32_t)(P.pred[p].cmp == 1);
+        const uint32_t is_eq = (uint32_t)(MDIM_SHAPE_OF(P).pred[p].cmp == 0), want_neg = (uint32_t)(MDIM_SHAPE_OF(P).pred[p].cmp == 1);
         if (lc == 0) {  // the vector axis is not involved: one test for all lanes
             const off_t d = s - rhs;
             const uint32_t zero = (uint32_t)(d == 0), neg = (uint32_t)(d < 0);
@@ -463,7 +522,7 @@ MDIM_FN int depth_delta(int opc, int aux) {
 template <int D, int NC, class S, int V, int MAXD, bool WIDE, int MAXR>
 MDIM_FN void exec_gather(const Program& P, ErrWord* err, const Instr& I, int slot, S (&st)[MAXD][V], const ThreadState<WIDE, MAXR>& ts) {
     if constexpr (sizeof(S) == 8 && D >= NC && NC >= 1) {
-        const Addr& A = P.addr[slot];
+        const Addr& A = MDIM_SHAPE_OF(P).addr[slot];  // gstride / bound / n_peers: shape-like; the pointer is read from P
         const int64_t base = (int64_t)addr_offset<WIDE, MAXR>(P, slot, ts);
         const int64_t s_in = inner_stride(P, slot);
         const int es = esize_of(I.dtype);
@@ -486,7 +545,7 @@ MDIM_FN void exec_gather(const Program& P, ErrWord* err, const Instr& I, int slo
                     const uint64_t p = (uint64_t)idx / P.peers.block;
                     v = ld_scalar<S>(P.peers.peer[p], (int64_t)((uint64_t)idx - p * P.peers.block), es);
                 } else {
-                    v = ld_scalar<S>(A.ptr, idx, es);
+                    v = ld_scalar<S>(P.addr[slot].ptr, idx, es);
                 }
             }
             st[D - NC][l] = v;
@@ -500,15 +559,15 @@ template <bool WIDE, int MAXR> MDIM_FN void carry_red(const Program& P, ThreadSt
     bool carry = true;
 #pragma unroll
     for (int a = MAXR - 1; a >= 0; --a) {
-        if (carry && a >= P.rank && a < P.rank + P.red_rank) {
+        if (carry && a >= MDIM_SHAPE_OF(P).rank && a < MDIM_SHAPE_OF(P).rank + MDIM_SHAPE_OF(P).red_rank) {
             ts.c[a] += 1;
-            if ((uint64_t)ts.c[a] >= P.length[a]) ts.c[a] = 0; else carry = false;
+            if ((uint64_t)ts.c[a] >= MDIM_SHAPE_OF(P).length[a]) ts.c[a] = 0; else carry = false;
         }
     }
 }
 template <bool WIDE, int MAXR> MDIM_FN void advance_red(const Program& P, ThreadState<WIDE, MAXR>& ts) {
     ts.rk += 1;
-    if ((uint64_t)ts.rk >= P.red_fast_len) { ts.rk = 0; carry_red<WIDE, MAXR>(P, ts); }
+    if ((uint64_t)ts.rk >= MDIM_SHAPE_OF(P).red_fast_len) { ts.rk = 0; carry_red<WIDE, MAXR>(P, ts); }
 }
 
 // Execute instruction I at compile-time stack depth D.  Returns the next pc.
@@ -518,7 +577,8 @@ template <bool WIDE, int MAXR> MDIM_FN void advance_red(const Program& P, Thread
 template <int D, class S, int V, int MAXD, bool WIDE, int MAXR, int SLOTK = -1>
 MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int op, int aux, int pc,
                        S (&st)[MAXD][V], ThreadState<WIDE, MAXR>& ts) {
-    const Instr& I = P.instr[pc];
+    const Instr& I = MDIM_SHAPE_OF(P).instr[pc];  // opcode operands (slot, n, source node) are shape-like ...
+    const uint64_t imm = P.instr[pc].imm;          // ... immediates are run-time data
     const int slot = SLOTK >= 0 ? SLOTK : (int)I.slot;  // (address slot; MASK / SELECT read I.slot themselves)
     int next = pc + 1;
     switch (opc) {
@@ -526,8 +586,9 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
             if constexpr (D < MAXD) {
                 const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, slot, ts);
                 if (ts.mask == (1u << V) - 1u) {  // (a compile-time fact in signatures without MASK)
-                    if (aux) ld_vector<S, V, true>(P.addr[slot].ptr, off, esize_of(dtype), st[D]);   // re-read operand: keep in L1
-                    else ld_vector<S, V, false>(P.addr[slot].ptr, off, esize_of(dtype), st[D]);      // read once: stream past L1
+                    const bool w256 = (P.flags & PF_VEC256) != 0;
+                    if (aux) ld_vector<S, V, true>(P.addr[slot].ptr, off, esize_of(dtype), st[D], w256);   // re-read operand: keep in L1
+                    else ld_vector<S, V, false>(P.addr[slot].ptr, off, esize_of(dtype), st[D], w256);      // read once: stream past L1
                 } else {  // under a Concat / lazy Diagonal: inactive lanes must not touch memory
                     const int es = esize_of(dtype);
 #pragma unroll
@@ -564,7 +625,7 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
         case OPC_CONST:  // Scalar::at (src/view.rs:1407)
             if constexpr (D < MAXD) {
 #pragma unroll
-                for (int l = 0; l < V; ++l) st[D][l] = (S)I.imm;
+                for (int l = 0; l < V; ++l) st[D][l] = (S)imm;
             }
             break;
         case OPC_UNARY:  // Map::at = f(v.at(i)) (src/view.rs:888), closed op set
@@ -590,7 +651,7 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
             if constexpr (D >= 1) {
                 const uint32_t m = eval_preds<V, WIDE, MAXR>(P, ts, I.slot, I.n);
 #pragma unroll
-                for (int l = 0; l < V; ++l) st[D - 1][l] = ((m >> l) & 1u) ? st[D - 1][l] : (S)I.imm;
+                for (int l = 0; l < V; ++l) st[D - 1][l] = ((m >> l) & 1u) ? st[D - 1][l] : (S)imm;
             }
             break;
         case OPC_SELECT2:  // Concat::at (src/view.rs:938-945): V where coord < len(V), else W
@@ -608,13 +669,13 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
         case OPC_FOLD_BEGIN:  // let mut s = init;  (the closure of rows().map(..))
             if constexpr (D < MAXD) {
 #pragma unroll
-                for (int l = 0; l < V; ++l) st[D][l] = (S)I.imm;
+                for (int l = 0; l < V; ++l) st[D][l] = (S)imm;
 #pragma unroll
                 for (int a = 0; a < MAXR; ++a)
-                    if (a >= P.rank) ts.c[a] = 0;
+                    if (a >= MDIM_SHAPE_OF(P).rank) ts.c[a] = 0;
                 ts.red_k = 0;
                 ts.rk = 0;
-                if (P.red_count == 0) next = I.slot;  // empty row: skip the body and its FOLD_STEP
+                if (MDIM_SHAPE_OF(P).red_count == 0) next = I.slot;  // empty row: skip the body and its FOLD_STEP
             }
             break;
         case OPC_FOLD_STEP:  // row.each(|x| s = s (op) x): sequential, index order (src/view.rs:250-252)
@@ -627,7 +688,7 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
                 }
                 advance_red<WIDE, MAXR>(P, ts);
                 ts.red_k += 1;
-                if (ts.red_k < P.red_count) next = I.slot;
+                if (ts.red_k < MDIM_SHAPE_OF(P).red_count) next = I.slot;
             }
             break;
     }
@@ -679,10 +740,10 @@ MDIM_FN void run_static(const Program& P, ErrWord* err, S (&st)[MAXD][V], Thread
             // Outer loop: the slower reduction axes (coordinates in c[], rare).  Inner loop: the fastest one,
             // where every coordinate in c[] is loop-invariant, so an operand's address is base + rk * rstride;
             // unrolled so that several steps' loads (independent of the add chain) are in flight together.
-            const uint64_t outer = P.red_fast_len ? P.red_count / P.red_fast_len : 0;
+            const uint64_t outer = MDIM_SHAPE_OF(P).red_fast_len ? MDIM_SHAPE_OF(P).red_count / MDIM_SHAPE_OF(P).red_fast_len : 0;
             for (uint64_t ko = 0; ko < outer; ++ko) {
 #pragma unroll 8
-                for (uint64_t k = 0; k < P.red_fast_len; ++k) {
+                for (uint64_t k = 0; k < MDIM_SHAPE_OF(P).red_fast_len; ++k) {
                     ts.rk = (typename CoordTraits<WIDE>::coord_t)k;
                     run_static<Sig, PC + 1, D + 1, END, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
                     if constexpr (D + 2 <= MAXD) {
@@ -753,19 +814,19 @@ MDIM_FN void eval_vector(const Program& P, void* out, ErrWord* err, uint64_t g) 
 #pragma unroll
     for (int a = 0; a < MAXR - 1; ++a) {  // axis 0 = the vector axis, peeled first
         coord_t q;
-        if constexpr (WIDE) q = rem / (coord_t)P.dec_len[a];
-        else q = fast_div(rem, P.div_mul[a], P.div_shr[a]);
-        const coord_t r = rem - q * (coord_t)P.dec_len[a];
-        ts.c[a] = r * (coord_t)P.dec_scale[a];
+        if constexpr (WIDE) q = rem / (coord_t)MDIM_SHAPE_OF(P).dec_len[a];
+        else q = fast_div(rem, MDIM_SHAPE_OF(P).div_mul[a], MDIM_SHAPE_OF(P).div_shr[a]);
+        const coord_t r = rem - q * (coord_t)MDIM_SHAPE_OF(P).dec_len[a];
+        ts.c[a] = r * (coord_t)MDIM_SHAPE_OF(P).dec_scale[a];
         rem = q;
     }
-    ts.c[MAXR - 1] = rem * (coord_t)P.dec_scale[MAXR - 1];
+    ts.c[MAXR - 1] = rem * (coord_t)MDIM_SHAPE_OF(P).dec_scale[MAXR - 1];
     S st[MAXD][V];
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {  // VPT consecutive vectors along the vector axis share one decode
         if constexpr (Sig::n > 0) run_static<Sig, 0, 0, Sig::n, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
         else run_interp<S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
-        st_vector<S, V>(out, ts.pos0, esize_of(P.out_dtype), st[0], true);
+        st_vector<S, V>(out, ts.pos0, esize_of(MDIM_SHAPE_OF(P).out_dtype), st[0], MDIM_STORE_STREAMING, (P.flags & PF_VEC256) != 0);
         if constexpr (VPT > 1) {
             ts.c[0] += (coord_t)V;
             ts.pos0 += (uint64_t)V;

@@ -68,8 +68,44 @@ std::mutex g_mu;
 std::map<std::string, Entry>& cache() { static std::map<std::string, Entry> c; return c; }
 bool verbose() { static const bool v = [] { const char* e = getenv("MDIM_JIT_VERBOSE"); return e && e[0] == '1'; }(); return v; }
 
-std::string make_source(const Plan& p, int maxr, int maxd) {
-    std::string s = "#include \"exec.cuh\"\nnamespace mdim { struct JitSig { static constexpr SigInstr code[] = {";
+// The shape-like part of the program as a constant-initialised device object (see MDIM_SHAPE_OF in exec.cuh).
+std::string make_shape_source(const Program& P) {
+    std::string s = "#include \"program.hpp\"\nnamespace mdim { __host__ __device__ constexpr Program mdim_make_shape() { Program p{};\n";
+    char b[320];
+    auto set = [&](const char* fmt, auto... args) { snprintf(b, sizeof b, fmt, args...); s += b; };
+    set("p.rank=%d; p.red_rank=%d; p.n_instr=%d; p.n_addr=%d; p.n_pred=%d; p.out_dtype=%d; p.vec=%d; p.vpt=%d;\n", P.rank, P.red_rank, P.n_instr, P.n_addr,
+        P.n_pred, P.out_dtype, P.vec, P.vpt);
+    set("p.n_vec=%lluull; p.red_count=%lluull; p.red_fast_len=%lluull;\n", (unsigned long long)P.n_vec, (unsigned long long)P.red_count,
+        (unsigned long long)P.red_fast_len);
+    for (int a = 0; a < kMaxRank; ++a)
+        set("p.length[%d]=%lluull; p.dec_len[%d]=%lluull; p.dec_scale[%d]=%uu; p.div_mul[%d]=%uu; p.div_shr[%d]=%uu;\n", a, (unsigned long long)P.length[a], a,
+            (unsigned long long)P.dec_len[a], a, P.dec_scale[a], a, P.div_mul[a], a, P.div_shr[a]);
+    for (int i = 0; i < P.n_instr; ++i) {
+        const Instr& I = P.instr[i];
+        set("p.instr[%d].opc=%d; p.instr[%d].dtype=%d; p.instr[%d].op=%d; p.instr[%d].aux=%d; p.instr[%d].slot=%d; p.instr[%d].n=%d;\n", i, (int)I.opc, i, (int)I.dtype, i,
+            (int)I.op, i, (int)I.aux, i, (int)I.slot, i, (int)I.n);
+    }
+    for (int i = 0; i < P.n_addr; ++i) {
+        const Addr& A = P.addr[i];
+        set("p.addr[%d].inner=%lldll; p.addr[%d].rstride=%lldll; p.addr[%d].n_peers=%d;\n", i, (long long)A.inner, i, (long long)A.rstride, i, A.n_peers);
+        for (int a = 0; a < kMaxRank; ++a) if (A.stride[a]) set("p.addr[%d].stride[%d]=%lldll;", i, a, (long long)A.stride[a]);
+        for (int c = 0; c < kMaxComp; ++c) if (A.gstride[c] || A.bound[c]) set("p.addr[%d].gstride[%d]=%lldll; p.addr[%d].bound[%d]=%lluull;", i, c, (long long)A.gstride[c], i, c, (unsigned long long)A.bound[c]);
+        s += "\n";
+    }
+    for (int i = 0; i < P.n_pred; ++i) {
+        const Pred& Q = P.pred[i];
+        set("p.pred[%d].lane_coef=%d; p.pred[%d].cmp=%d; p.pred[%d].rhs=%lldll;", i, Q.lane_coef, i, Q.cmp, i, (long long)Q.rhs);
+        for (int a = 0; a < kMaxRank; ++a) if (Q.coef[a]) set("p.pred[%d].coef[%d]=%d;", i, a, Q.coef[a]);
+        s += "\n";
+    }
+    s += "return p; } }\nstatic __device__ const mdim::Program mdim_jit_shape = mdim::mdim_make_shape();\n#define MDIM_SHAPE_OF(P) (mdim_jit_shape)\n";
+    return s;
+}
+
+std::string make_source(const Plan& p, int maxr, int maxd, bool with_shape) {
+    std::string s = with_shape ? make_shape_source(p.prog) : std::string();
+    if (const char* e = getenv("MDIM_JIT_STORE_DEFAULT")) if (e[0] == '1') s = "#define MDIM_STORE_STREAMING false\n" + s;
+    s += "#include \"exec.cuh\"\nnamespace mdim { struct JitSig { static constexpr SigInstr code[] = {";
     char buf[64];
     for (int i = 0; i < p.prog.n_instr; ++i) {
         const Instr& I = p.prog.instr[i];
@@ -78,7 +114,7 @@ std::string make_source(const Plan& p, int maxr, int maxd) {
     }
     snprintf(buf, sizeof buf, "}; static constexpr int n = %d; }; }\n", p.prog.n_instr);
     s += buf;
-    char k[512];
+    char k[640];
     snprintf(k, sizeof k,
              "extern \"C\" __global__ void __launch_bounds__(256) mdim_jit_kernel(const __grid_constant__ mdim::Program P, void* __restrict__ out, "
              "mdim::ErrWord* __restrict__ err, unsigned long long g_begin, unsigned long long g_end) {\n"
@@ -90,13 +126,23 @@ std::string make_source(const Plan& p, int maxr, int maxd) {
     return s;
 }
 
+// cache key of the shape-like part: the program with every run-time field (pointers, offsets, immediates) zeroed
+std::string shape_key(const Program& P) {
+    Program q = P;
+    q.flags &= PF_VEC256; q.explain_pos = 0;
+    for (int i = 0; i < kMaxInstr; ++i) q.instr[i].imm = 0;
+    for (int i = 0; i < kMaxAddr; ++i) { q.addr[i].ptr = nullptr; q.addr[i].offset = 0; }
+    memset(&q.peers, 0, sizeof q.peers);
+    return std::string((const char*)&q, sizeof q);
+}
+
 }  // namespace
 
 // NVRTC: source -> sm_100a cubin.  Returns false (and the compiler log) on failure.
-static bool compile_cubin(const Plan& p, int maxr, int maxd, std::vector<char>& cubin, std::string& log_out) {
+static bool compile_cubin(const Plan& p, int maxr, int maxd, bool with_shape, std::vector<char>& cubin, std::string& log_out) {
     static Nvrtc nv;
     if (!nv.ok) { log_out = "NVRTC (libnvrtc.so.12) is not available"; return false; }
-    const std::string src = make_source(p, maxr, maxd);
+    const std::string src = make_source(p, maxr, maxd, with_shape);
     const char* headers[] = {kSrcExec, kSrcProgram, kSrcMdimH, kStdint, kStddef, kString};
     const char* names[] = {"exec.cuh", "program.hpp", "../../include/mdim.h", "stdint.h", "stddef.h", "string.h"};
     nvrtcProgram prog = nullptr;
@@ -114,6 +160,12 @@ static bool compile_cubin(const Plan& p, int maxr, int maxd, std::vector<char>& 
     if (nv.cubin_size(prog, &n) == NVRTC_SUCCESS && n) { cubin.resize(n); if (nv.cubin(prog, cubin.data()) != NVRTC_SUCCESS) cubin.clear(); }
     nv.destroy(&prog);
     if (cubin.empty()) { log_out = "no cubin produced"; return false; }
+    if (const char* dir = getenv("MDIM_JIT_DUMP")) {  // for cuobjdump -sass
+        static int counter = 0;
+        char path[512];
+        snprintf(path, sizeof path, "%s/mdim_jit_%d%s.cubin", dir, counter++, with_shape ? "_shape" : "");
+        if (FILE* f = fopen(path, "wb")) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
+    }
     return true;
 }
 
@@ -126,15 +178,21 @@ int jit_compile_check(const Plan& p, char* log, size_t log_len) {
     if ((p.kind != KK_STREAM && p.kind != KK_GENERIC) || p.vpt != 1) { if (log && log_len) snprintf(log, log_len, "not an evaluator plan"); return MDIM_ERR_UNSUPPORTED; }
     int maxr, maxd; jit_shape(p, maxr, maxd);
     std::vector<char> cubin; std::string msg;
-    const bool ok = compile_cubin(p, maxr, maxd, cubin, msg);
+    bool ok = compile_cubin(p, maxr, maxd, false, cubin, msg);
+    if (ok && !p.wide) ok = compile_cubin(p, maxr, maxd, true, cubin, msg);  // and the shape-specialised form
     if (log && log_len) snprintf(log, log_len, "%s", ok ? "ok" : msg.c_str());
     if (ok) return MDIM_OK;
     return msg.rfind("NVRTC", 0) == 0 ? MDIM_ERR_UNSUPPORTED : MDIM_ERR_INVALID;
 }
 
-// Returns a kernel specialised for the plan's op sequence, or nullptr (use the interpreter).
+// Returns a kernel specialised for the plan, or nullptr (use the pre-built signature / the interpreter).
+//   level 1: the op sequence (only for plans without a pre-built signature)
+//   level 2: the op sequence AND the shape — strides, lengths, dividers and predicates become immediates.
+//            Built when the same (ops, shape) has been collected MDIM_JIT_SHAPES times (default 2; 0 = never,
+//            1 = at once) and the chain is a rank >= 2 evaluator plan, where the coordinate decode dominates.
 void* jit_kernel_for(const Plan& p) {
     static const bool enabled = [] { const char* e = getenv("MDIM_JIT"); return !(e && e[0] == '0'); }();
+    static const int shape_after = [] { const char* e = getenv("MDIM_JIT_SHAPES"); return e ? atoi(e) : 2; }();
     if (!enabled || (p.kind != KK_STREAM && p.kind != KK_GENERIC) || p.vpt != 1) return nullptr;
     int maxr, maxd; jit_shape(p, maxr, maxd);
     std::string key(p.sig, p.sig + p.sig_len);
@@ -142,26 +200,38 @@ void* jit_kernel_for(const Plan& p) {
     snprintf(tail, sizeof tail, "|%d|%d|%d|%d|%d", p.slot_bytes, p.vec, maxd, p.wide, maxr);
     key += tail;
     std::lock_guard<std::mutex> lock(g_mu);
-    Entry& e = cache()[key];
-    if (e.kernel) return (void*)e.kernel;
-    if (e.failed) return nullptr;
-    e.failed = true;  // until proven otherwise
-    std::vector<char> cubin; std::string msg;
-    if (!compile_cubin(p, maxr, maxd, cubin, msg)) {
-        if (verbose()) fprintf(stderr, "mdim jit: %s — using the interpreter\n", msg.c_str());
-        return nullptr;
+    auto build = [&](Entry& e, bool with_shape) -> void* {
+        if (e.kernel) return (void*)e.kernel;
+        if (e.failed) return nullptr;
+        e.failed = true;  // until proven otherwise
+        std::vector<char> cubin; std::string msg;
+        if (!compile_cubin(p, maxr, maxd, with_shape, cubin, msg)) {
+            if (verbose()) fprintf(stderr, "mdim jit: %s — not specialised\n", msg.c_str());
+            return nullptr;
+        }
+        cudaLibrary_t lib = nullptr;
+        cudaKernel_t kern = nullptr;
+        if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
+            cudaLibraryGetKernel(&kern, lib, "mdim_jit_kernel") != cudaSuccess) {
+            cudaGetLastError();
+            if (verbose()) fprintf(stderr, "mdim jit: loading the cubin failed — not specialised\n");
+            return nullptr;
+        }
+        e.kernel = kern; e.library = lib; e.failed = false;
+        if (verbose())
+            fprintf(stderr, "mdim jit: specialised %d instructions (slot %d, V %d, depth %d, rank %d%s)%s\n", p.prog.n_instr, p.slot_bytes * 8, p.vec, maxd, maxr,
+                    p.wide ? ", wide" : "", with_shape ? " for one shape" : "");
+        return (void*)kern;
+    };
+    if (shape_after > 0 && p.kind == KK_GENERIC && !p.wide && !(p.prog.flags & PF_EXPLAIN)) {
+        static std::map<std::string, int> seen;
+        const std::string skey = key + "#" + shape_key(p.prog);
+        if (++seen[skey] >= shape_after) {
+            if (void* k = build(cache()[skey], true)) return k;
+        }
     }
-    cudaLibrary_t lib = nullptr;
-    cudaKernel_t kern = nullptr;
-    if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
-        cudaLibraryGetKernel(&kern, lib, "mdim_jit_kernel") != cudaSuccess) {
-        cudaGetLastError();
-        if (verbose()) fprintf(stderr, "mdim jit: loading the cubin failed, using the interpreter\n");
-        return nullptr;
-    }
-    e.kernel = kern; e.library = lib; e.failed = false;
-    if (verbose()) fprintf(stderr, "mdim jit: specialised %d instructions (slot %d, V %d, depth %d, rank %d%s)\n", p.prog.n_instr, p.slot_bytes * 8, p.vec, maxd, maxr, p.wide ? ", wide" : "");
-    return (void*)kern;
+    if (p.static_id >= 0) return nullptr;  // the pre-built signature serves it
+    return build(cache()[key], false);
 }
 
 }  // namespace mdim

@@ -292,6 +292,12 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
                 for (int g = 0; g < n_axes && ok; ++g)
                     if (g != rank - 1 && ((cstride[ni][g] * es) % align) != 0) ok = false;
                 opc = ok ? OPC_LEAF_VEC : OPC_LEAF_STRIDED;
+                if (ok) {  // 256-bit accesses need every vector of this operand 32-byte aligned
+                    bool ok32 = (((uintptr_t)A.ptr + (uintptr_t)(A.offset * es)) % 32) == 0;
+                    for (int g = 0; g < n_axes && ok32; ++g)
+                        if (g != rank - 1 && ((cstride[ni][g] * es) % 32) != 0) ok32 = false;
+                    if (!ok32) plan->vec256_ok = 0;
+                }
             } else opc = OPC_LEAF_STRIDED;
             in.opc = (uint8_t)opc; in.slot = (uint16_t)slot;
             if (opc == OPC_LEAF_VEC)  // re-read along a broadcast output axis => worth keeping in L1
@@ -455,8 +461,9 @@ int Builder::emit() {
     if (rank > 0) {
         const int cand32[3] = {8, 4, 1}, cand64[3] = {4, 2, 1};
         const int* cand = slot == 4 ? cand32 : cand64;
+        static const int max_bytes = [] { const char* e = getenv("MDIM_MAX_VEC_BYTES"); return e ? atoi(e) : 32; }();
         for (int i = 0; i < 3; ++i)
-            if (len[rank - 1] % (uint64_t)cand[i] == 0) { V = cand[i]; break; }
+            if (cand[i] * slot <= max_bytes && len[rank - 1] % (uint64_t)cand[i] == 0) { V = cand[i]; break; }
     }
     // A fold walks its reduction axes sequentially inside one thread, so the output is the only source of
     // parallelism: prefer narrower vectors until there are enough threads to fill the machine.
@@ -508,6 +515,7 @@ int Builder::emit() {
         find_divisor((uint32_t)std::min<uint64_t>(L, 0x7fffffffull), &P.div_mul[a], &P.div_shr[a]);
     }
     depth = 0; max_depth = 0;
+    plan->vec256_ok = (V * slot == 32) ? 1 : 0;
     int st = gen(root, 0, 0);
     if (st) return st;
     if (depth != 1) return why.fail(MDIM_ERR_INVALID, "internal: program leaves depth %d", depth);

@@ -75,6 +75,7 @@ struct PeerTab {
 
 enum ProgFlags : uint32_t {
     PF_EXPLAIN = 1u,  // single-lane rerun that records mdim_error_info details
+    PF_VEC256 = 2u,   // every vector operand and the output are 32-byte aligned: 256-bit loads / stores
 };
 
 struct Program {
@@ -162,6 +163,7 @@ struct Plan {
     int32_t vpt;         // vectors per thread trip
     int32_t wide;        // 64-bit coordinates/strides
     int32_t n_axes;      // rank + red_rank after canonicalisation (selects the MAXR instantiation)
+    int32_t vec256_ok;   // every LEAF_VEC operand is 32-byte aligned (the output is checked at launch)
     int32_t max_depth;
     int32_t static_id;   // index into the signature registry, -1 = interpreted
     uint64_t out_elems;

@@ -67,6 +67,7 @@ extern "C" int mdim_emu_collect(const mdim_expr* e, void* out, uint32_t flags, m
     ErrWord err;
     memset(&err, 0, sizeof err);
     err.pos = ~0ull;
+    if (plan->vec256_ok && ((uintptr_t)out % 32) == 0) plan->prog.flags |= PF_VEC256;  // as mdim_collect does at launch
     st = run(*plan, plan->prog, out, &err, 0, plan->prog.n_vec);
     if (st == MDIM_OK && err.pos != ~0ull) {
         const uint64_t pos = err.pos;
