@@ -89,6 +89,10 @@ MDIM_FN void ld128_cached(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, 
 // instruction covers 1 KB of whole sectors.  With two 128-bit accesses per thread every instruction touches
 // HALF of each 32-byte sector: harmless for reads, but a write-only stream then runs at 4.0 instead of
 // 7.6 TB/s (profiles/: iota collect), and the write-bound rank-5 chain at 4.2 instead of 6.4.
+#if defined(MDIM_NO_VEC256)  // an NVRTC older than 12.9 (PTX < 8.8) has no 256-bit vector accesses: two 128-bit ones
+MDIM_FN void ld256_stream(const void* p, uint32_t (&r)[8]) { ld128_stream(p, r[0], r[1], r[2], r[3]); ld128_stream((const char*)p + 16, r[4], r[5], r[6], r[7]); }
+MDIM_FN void ld256_cached(const void* p, uint32_t (&r)[8]) { ld128_cached(p, r[0], r[1], r[2], r[3]); ld128_cached((const char*)p + 16, r[4], r[5], r[6], r[7]); }
+#else
 MDIM_FN void ld256_stream(const void* p, uint32_t (&r)[8]) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
@@ -97,10 +101,16 @@ MDIM_FN void ld256_cached(const void* p, uint32_t (&r)[8]) {
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
 }
+#endif
+#if defined(MDIM_NO_VEC256)
+MDIM_FN void st128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool cs);
+MDIM_FN void st256(void* p, const uint32_t (&r)[8], bool cs) { st128(p, r[0], r[1], r[2], r[3], cs); st128((char*)p + 16, r[4], r[5], r[6], r[7], cs); }
+#else
 MDIM_FN void st256(void* p, const uint32_t (&r)[8], bool cs) {
     if (cs) asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
     else asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
+#endif
 MDIM_FN void ld64_stream(const void* p, uint32_t& a, uint32_t& b) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
 }

@@ -46,9 +46,13 @@ struct Nvrtc {
     decltype(&nvrtcGetCUBIN) cubin = nullptr;
     decltype(&nvrtcGetProgramLogSize) log_size = nullptr;
     decltype(&nvrtcGetProgramLog) log = nullptr;
+    decltype(&nvrtcVersion) version = nullptr;
     bool ok = false;
+    bool has_vec256 = false;  // PTX ISA 8.8 (CUDA 12.9): 256-bit vector loads / stores
     Nvrtc() {
-        const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+        // the toolkit's own copy first: a process that imported torch already has torch's bundled (older) NVRTC
+        // loaded under the same soname, and a lookup by name would hand that one back
+        const char* names[] = {"/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so.12", "libnvrtc.so"};
         for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (lib) break; }
         if (!lib) return;
         create = (decltype(create))dlsym(lib, "nvrtcCreateProgram");
@@ -58,7 +62,10 @@ struct Nvrtc {
         cubin = (decltype(cubin))dlsym(lib, "nvrtcGetCUBIN");
         log_size = (decltype(log_size))dlsym(lib, "nvrtcGetProgramLogSize");
         log = (decltype(log))dlsym(lib, "nvrtcGetProgramLog");
+        version = (decltype(version))dlsym(lib, "nvrtcVersion");
         ok = create && compile && destroy && cubin_size && cubin && log_size && log;
+        int major = 0, minor = 0;
+        if (version && version(&major, &minor) == NVRTC_SUCCESS) has_vec256 = major > 12 || (major == 12 && minor >= 9);
     }
 };
 
@@ -147,8 +154,8 @@ static bool compile_cubin(const Plan& p, int maxr, int maxd, bool with_shape, st
     const char* names[] = {"exec.cuh", "program.hpp", "../../include/mdim.h", "stdint.h", "stddef.h", "string.h"};
     nvrtcProgram prog = nullptr;
     if (nv.create(&prog, src.c_str(), "mdim_jit.cu", 6, headers, names) != NVRTC_SUCCESS) { log_out = "nvrtcCreateProgram failed"; return false; }
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo"};
-    const nvrtcResult rc = nv.compile(prog, 4, opts);
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-DMDIM_NO_VEC256"};
+    const nvrtcResult rc = nv.compile(prog, nv.has_vec256 ? 4 : 5, opts);
     if (rc != NVRTC_SUCCESS) {
         size_t n = 0; nv.log_size(prog, &n);
         std::vector<char> log(n + 1, 0); nv.log(prog, log.data());
