@@ -233,6 +233,7 @@ void* jit_kernel_for(const Plan& p) {
     if (shape_after > 0 && p.kind == KK_GENERIC && !p.wide && !(p.prog.flags & PF_EXPLAIN)) {
         static std::map<std::string, int> seen;
         const std::string skey = key + "#" + shape_key(p.prog);
+        if (seen.size() > 4096) seen.clear();  // a workload of ever-changing shapes must not grow this without bound
         if (++seen[skey] >= shape_after) {
             if (void* k = build(cache()[skey], true)) return k;
         }

@@ -408,3 +408,18 @@ print("ok")
     env = dict(os.environ, MDIM_FOLD_MODE=mode)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_shape_specialised_kernels_on_first_use():
+    """By default a rank-N chain is specialised on its shape the SECOND time it is collected, which most
+    tests never reach; MDIM_JIT_SHAPES=1 specialises at once, so the same parity tests then run through the
+    shape-specialised kernels (strides, dividers and predicates as immediates)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MDIM_JIT_SHAPES="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-k",
+                        "(rank5 or mixed_strides or concat or diagonal_guards or transpose_batched or fold_over_outermost or two_components) and gpu"],
+                       env=env, capture_output=True, text=True, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
