@@ -181,9 +181,11 @@ int launch_eval(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err, bool expl
     if (jit) {
         unsigned long long a0 = g0, a1 = g1;
         void* args[] = {(void*)&q, (void*)&out, (void*)&err, (void*)&a0, (void*)&a1};
-        CU(ctx, cudaLaunchKernel((const void*)jit, dim3((unsigned)grid), dim3(kEvalThreads), args, 0, ctx->stream));
+        cudaLaunchConfig_t cfg; cudaLaunchAttribute attr;
+        pdl_config(cfg, attr, dim3((unsigned)grid), dim3(kEvalThreads), 0, ctx->stream);
+        CU(ctx, cudaLaunchKernelExC(&cfg, (const void*)jit, args));
     } else {
-        v->fn<<<grid, kEvalThreads, 0, ctx->stream>>>(q, out, err, g0, g1);
+        CU(ctx, launch_pdl(v->fn, dim3((unsigned)grid), dim3(kEvalThreads), 0, ctx->stream, q, out, err, g0, g1));
     }
     ctx->launches++;
     CU(ctx, cudaGetLastError());

@@ -121,10 +121,11 @@ std::string make_source(const Plan& p, int maxr, int maxd, bool with_shape) {
     }
     snprintf(buf, sizeof buf, "}; static constexpr int n = %d; }; }\n", p.prog.n_instr);
     s += buf;
-    char k[640];
+    char k[900];
     snprintf(k, sizeof k,
              "extern \"C\" __global__ void __launch_bounds__(256) mdim_jit_kernel(const __grid_constant__ mdim::Program P, void* __restrict__ out, "
              "mdim::ErrWord* __restrict__ err, unsigned long long g_begin, unsigned long long g_end) {\n"
+             "  asm volatile(\"griddepcontrol.wait;\" ::: \"memory\"); asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");\n"
              "  const unsigned long long step = (unsigned long long)gridDim.x * 256ull;\n"
              "  for (unsigned long long g = g_begin + (unsigned long long)blockIdx.x * 256ull + threadIdx.x; g < g_end; g += step)\n"
              "    mdim::eval_vector<mdim::JitSig, %s, %d, %d, %s, %d, 1>(P, out, err, g);\n}\n",

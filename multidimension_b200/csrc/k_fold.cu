@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(kFoldThreads)
 k_fold_rows(const __grid_constant__ FoldRowsPlan R, void* __restrict__ out_v, int n_warps, int stages, int ch, int skew, uint32_t q4_mul,
             uint32_t q4_shr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_entry();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp >= n_warps) return;
     const uint32_t tile_words = (uint32_t)kRowsPerTile * (uint32_t)ch;
@@ -248,6 +249,7 @@ template <int L, bool FAST>
 __global__ void __launch_bounds__(256) k_fold_regs(const __grid_constant__ FoldRowsPlan R, void* __restrict__ out_v) {
     constexpr int M = 8;         // 16-byte chunks per lane
     constexpr int RPW = 32 / L;  // rows per warp
+    pdl_entry();
     const int lane = threadIdx.x & 31, j = lane % L, grp = lane / L;
     const uint64_t warp = (uint64_t)blockIdx.x * (256 / 32) + (threadIdx.x >> 5);
     const uint64_t row = warp * RPW + grp;
@@ -320,12 +322,12 @@ template <bool FAST> static bool launch_regs(const FoldRowsPlan& R, void* out, c
     if (ctas > 0x7fffffffull) return false;
     const dim3 grid((unsigned)ctas), block(256);
     switch (L) {
-        case 1: k_fold_regs<1, FAST><<<grid, block, 0, stream>>>(R, out); break;
-        case 2: k_fold_regs<2, FAST><<<grid, block, 0, stream>>>(R, out); break;
-        case 4: k_fold_regs<4, FAST><<<grid, block, 0, stream>>>(R, out); break;
-        case 8: k_fold_regs<8, FAST><<<grid, block, 0, stream>>>(R, out); break;
-        case 16: k_fold_regs<16, FAST><<<grid, block, 0, stream>>>(R, out); break;
-        default: k_fold_regs<32, FAST><<<grid, block, 0, stream>>>(R, out); break;
+        case 1: launch_pdl(k_fold_regs<1, FAST>, grid, block, 0, stream, R, out); break;
+        case 2: launch_pdl(k_fold_regs<2, FAST>, grid, block, 0, stream, R, out); break;
+        case 4: launch_pdl(k_fold_regs<4, FAST>, grid, block, 0, stream, R, out); break;
+        case 8: launch_pdl(k_fold_regs<8, FAST>, grid, block, 0, stream, R, out); break;
+        case 16: launch_pdl(k_fold_regs<16, FAST>, grid, block, 0, stream, R, out); break;
+        default: launch_pdl(k_fold_regs<32, FAST>, grid, block, 0, stream, R, out); break;
     }
     return true;
 }
@@ -371,7 +373,7 @@ void launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream
     const uint32_t q4_mul = (uint32_t)(((1ull << (31 + lg)) + q4 - 1) / q4);
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, kFoldThreads, smem, stream>>>(R, out, n_warps, stages, ch, skew, q4_mul, q4_shr);
+        launch_pdl(kern, dim3(grid), dim3(kFoldThreads), smem, stream, R, out, n_warps, stages, ch, skew, q4_mul, q4_shr);
     };
     if (fast) go(k_fold_rows<true>); else go(k_fold_rows<false>);
 }

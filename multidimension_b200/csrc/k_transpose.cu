@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(kTrThreads) k_transpose(const __grid_constant_
     constexpr int TB = 64;        // tile extent along B (rows of the source)
     constexpr int PA = TA / 32;   // read-phase passes along A
     __shared__ __align__(16) uint32_t smem[TB * 64];
+    pdl_entry();
 
     const char* __restrict__ src = (const char*)T.src;
     char* __restrict__ out = (char*)out_v;
@@ -145,6 +146,7 @@ template <int ES>
 __global__ void __launch_bounds__(kTrThreads) k_transpose_pipe(const __grid_constant__ TransposePlan T, void* __restrict__ out_v) {
     constexpr int CH = 16 / ES, EW = ES / 4, TA = 16 * CH, TB = 64, PA = TA / 32;
     extern __shared__ __align__(16) uint32_t ring[];  // kTrStages x (TB x 64 words)
+    pdl_entry();
     const char* __restrict__ src = (const char*)T.src;
     char* __restrict__ out = (char*)out_v;
     const int tid = threadIdx.x;
@@ -243,16 +245,16 @@ void launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t 
     const bool vec = transpose_vec_ok(T, out);
     constexpr int smem = kTrStages * 64 * 64 * 4;
     if (vec && use_pipe()) {
-        if (T.esize == 4) k_transpose_pipe<4><<<grid, kTrThreads, smem, stream>>>(T, out);
-        else k_transpose_pipe<8><<<grid, kTrThreads, smem, stream>>>(T, out);
+        if (T.esize == 4) launch_pdl(k_transpose_pipe<4>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);
+        else launch_pdl(k_transpose_pipe<8>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);
         return;
     }
     if (T.esize == 4) {
-        if (vec) k_transpose<4, true><<<grid, kTrThreads, 0, stream>>>(T, out);
-        else k_transpose<4, false><<<grid, kTrThreads, 0, stream>>>(T, out);
+        if (vec) launch_pdl(k_transpose<4, true>, dim3(grid), dim3(kTrThreads), 0, stream, T, out);
+        else launch_pdl(k_transpose<4, false>, dim3(grid), dim3(kTrThreads), 0, stream, T, out);
     } else {
-        if (vec) k_transpose<8, true><<<grid, kTrThreads, 0, stream>>>(T, out);
-        else k_transpose<8, false><<<grid, kTrThreads, 0, stream>>>(T, out);
+        if (vec) launch_pdl(k_transpose<8, true>, dim3(grid), dim3(kTrThreads), 0, stream, T, out);
+        else launch_pdl(k_transpose<8, false>, dim3(grid), dim3(kTrThreads), 0, stream, T, out);
     }
 }
 
