@@ -113,7 +113,7 @@ struct mdim_ctx {
     HostPipe pipe;
     int eval_ctas_per_sm = 8;
     int eval_waves = 0;  // 0 = one trip per thread (non-persistent)
-    int tr_ctas_per_sm = 0;
+    int tr_ctas_cap = 0;                               // MDIM_TR_CTAS_PER_SM
     uint64_t pos_base = 0;  // applied to collects issued while a host collect is chunking
     size_t host_chunk_bytes = 128u << 20;  // measured: 8 MB 60.7, 32 MB 73.1, 128 MB 75.8, 512 MB 76.3 GB/s end to end
 };
@@ -196,8 +196,10 @@ int launch_plan(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err) {
     switch (p.kind) {
         case KK_EMPTY: return MDIM_OK;
         case KK_TRANSPOSE: {
-            if (!ctx->tr_ctas_per_sm) ctx->tr_ctas_per_sm = transpose_max_ctas_per_sm();
-            const uint64_t cap = (uint64_t)ctx->sm_count * ctx->tr_ctas_per_sm;
+            // Not persistent: far more CTAs than fit at once, so the hardware scheduler balances the tail.
+            // Measured (B200, 16384^2 f32): 8/SM (resident set) 5.71 TB/s, 64/SM 6.18, 128/SM 6.32, one CTA per tile 6.35.
+            const int per_sm = ctx->tr_ctas_cap > 0 ? ctx->tr_ctas_cap : 128;
+            const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
             const int grid = (int)std::min<uint64_t>(p.tr.n_tiles, std::max<uint64_t>(cap, 1));
             launch_transpose(p.tr, out, grid, ctx->stream);
             ctx->launches++;
@@ -300,7 +302,7 @@ int mdim_init(int device, mdim_ctx** out) {
     ctx->hbm = prop.totalGlobalMem;
     ctx->eval_ctas_per_sm = env_int("MDIM_EVAL_CTAS_PER_SM", 8);
     ctx->eval_waves = env_int("MDIM_EVAL_WAVES", 0);
-    ctx->tr_ctas_per_sm = env_int("MDIM_TR_CTAS_PER_SM", 0);
+    ctx->tr_ctas_cap = env_int("MDIM_TR_CTAS_PER_SM", 0);
     ctx->host_chunk_bytes = (size_t)std::max(1, env_int("MDIM_HOST_CHUNK_MB", 128)) << 20;
     bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&ctx->d_err, sizeof(ErrWord) * kErrSlots) == cudaSuccess &&

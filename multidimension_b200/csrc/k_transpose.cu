@@ -6,8 +6,8 @@
 //
 //   out[batch, a, b]  (b has out stride 1)   =   src[batch', b, a]  (a has src stride 1)
 //
-// One CTA moves one tile of 64 B-rows x 16 chunks (16 bytes each) of A: 64x64 4-byte elements or
-// 64x32 8-byte elements, 16 KB of shared memory, both global directions 128-bit and coalesced:
+// One CTA moves one tile of TB B-rows x TAC chunks (16 bytes each) of A; the default is 64 rows x 16 chunks, i.e.
+// 64x64 4-byte or 64x32 8-byte elements, 16 KB of shared memory, both global directions 128-bit and coalesced:
 //   load : each thread reads 16 B along A (a warp covers 2 source rows x 256 B) and writes them
 //          with ONE 16-byte shared store at row b, chunk (a_chunk ^ swz(b));
 //   store: each thread assembles 16 B along B from CH scalar shared loads (one per source row) and
@@ -15,6 +15,8 @@
 // Swizzle swz(b) = (b / CH) & 7 makes both shared phases bank-conflict-free: a quarter warp's
 // 16-byte stores hit 8 distinct chunks, and in the read phase the 32 lanes (8 b-groups x 4 a's)
 // hit 8 distinct chunks x 4 distinct words.
+// The grid is NOT persistent (up to 128 CTAs per SM are launched, each takes 1-4 tiles): the hardware scheduler
+// then balances the tail, worth +11 % at 16384^2 and +8 % at 4096^2 over one resident set of CTAs.
 // Bit-exact by construction (pure data movement).  HBM-bound: algorithmic bytes = 2 x elements.
 #include <stdlib.h>
 
@@ -22,22 +24,29 @@
 
 namespace mdim {
 
-template <int ES, bool VEC>
-__global__ void __launch_bounds__(kTrThreads) k_transpose(const __grid_constant__ TransposePlan T, void* __restrict__ out_v) {
-    constexpr int CH = 16 / ES;   // elements per 16-byte chunk
-    constexpr int EW = ES / 4;    // 32-bit words per element
-    constexpr int TA = 16 * CH;   // tile extent along A (elements)
-    constexpr int TB = 64;        // tile extent along B (rows of the source)
-    constexpr int PA = TA / 32;   // read-phase passes along A
-    __shared__ __align__(16) uint32_t smem[TB * 64];
+constexpr int tr_min_ctas(int smem_bytes) { return 227 * 1024 / (smem_bytes + 1024) > 8 ? 8 : 227 * 1024 / (smem_bytes + 1024); }
+
+template <int ES, bool VEC, int TAC, int TB>
+__global__ void __launch_bounds__(kTrThreads, tr_min_ctas(TB * TAC * 16)) k_transpose(const __grid_constant__ TransposePlan T, void* __restrict__ out_v) {
+    constexpr int CH = 16 / ES;            // elements per 16-byte chunk
+    constexpr int EW = ES / 4;             // 32-bit words per element
+    constexpr int TA = TAC * CH;           // tile extent along A (elements); TAC chunks = TAC*16 bytes per source run
+    constexpr int RW = TAC * 4;            // shared row pitch in words
+    constexpr int RPP = kTrThreads / TAC;  // source rows per load pass
+    constexpr int NP = TB / RPP;           // passes per tile (load and store phases alike)
+    constexpr int LB = NP > 8 ? 8 : NP;    // loads kept in registers at once
+    constexpr int PA = TA / 32;            // store-phase groups along A
+    constexpr int NBG = TB / (8 * CH);     // store-phase groups of 8 output chunks along B
+    static_assert(NP * RPP == TB && PA * NBG == NP && TAC % 8 == 0, "tile shape");
+    extern __shared__ __align__(16) uint32_t smem[];  // TB x RW words
     pdl_entry();
 
     const char* __restrict__ src = (const char*)T.src;
     char* __restrict__ out = (char*)out_v;
     const int tid = threadIdx.x;
     // load-phase coordinates
-    const int aq = tid & 15, br = tid >> 4;
-    // read-phase coordinates
+    const int aq = tid % TAC, br = tid / TAC;
+    // store-phase coordinates
     const int lane = tid & 31, w = tid >> 5;
     const int bq_lo = lane & 7, a_lo = lane >> 3;
 
@@ -65,56 +74,62 @@ __global__ void __launch_bounds__(kTrThreads) k_transpose(const __grid_constant_
             }
         }
         const uint64_t a0 = ta * TA, b0 = tb * TB;
+        const bool full = a0 + TA <= T.len_a && b0 + TB <= T.len_b;  // interior tile: no per-access bounds tests
 
         // ---- load: global (contiguous along A) -> swizzled shared --------------------------------
-        uint4 v[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int b_l = p * 16 + br;
-            const uint64_t b = b0 + b_l, a = a0 + (uint64_t)aq * CH;
-            const int64_t e = src_base + (int64_t)b * T.src_stride_b + (int64_t)a;
-            v[p] = make_uint4(0, 0, 0, 0);
-            if constexpr (VEC) {
-                if (b < T.len_b && a < T.len_a)
-                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                 : "=r"(v[p].x), "=r"(v[p].y), "=r"(v[p].z), "=r"(v[p].w) : "l"(src + e * ES));
-            } else {
-                uint32_t wds[4] = {0, 0, 0, 0};
+        for (int h = 0; h < NP; h += LB) {
+            uint4 v[LB];
 #pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                    if (b < T.len_b && a + i < T.len_a) {
-                        if constexpr (ES == 4) wds[i] = __ldg((const uint32_t*)(src + (e + i) * 4));
-                        else { const uint2 t = __ldg((const uint2*)(src + (e + i) * 8)); wds[2 * i] = t.x; wds[2 * i + 1] = t.y; }
+            for (int q = 0; q < LB; ++q) {
+                const int b_l = (h + q) * RPP + br;
+                const uint64_t b = b0 + b_l, a = a0 + (uint64_t)aq * CH;
+                const int64_t e = src_base + (int64_t)b * T.src_stride_b + (int64_t)a;
+                v[q] = make_uint4(0, 0, 0, 0);
+                if constexpr (VEC) {
+                    if (full || (b < T.len_b && a < T.len_a))
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w) : "l"(src + e * ES));
+                } else {
+                    uint32_t wds[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        if (b < T.len_b && a + i < T.len_a) {
+                            if constexpr (ES == 4) wds[i] = __ldg((const uint32_t*)(src + (e + i) * 4));
+                            else { const uint2 t = __ldg((const uint2*)(src + (e + i) * 8)); wds[2 * i] = t.x; wds[2 * i + 1] = t.y; }
+                        }
                     }
+                    v[q] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
                 }
-                v[p] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
             }
-        }
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int b_l = p * 16 + br;
-            const int chunk = aq ^ ((b_l / CH) & 7);
-            *reinterpret_cast<uint4*>(&smem[b_l * 64 + chunk * 4]) = v[p];
+            for (int q = 0; q < LB; ++q) {
+                const int b_l = (h + q) * RPP + br;
+                const int chunk = aq ^ ((b_l / CH) & 7);
+                *reinterpret_cast<uint4*>(&smem[b_l * RW + chunk * 4]) = v[q];
+            }
         }
         __syncthreads();
 
         // ---- store: shared (gathered along B) -> global (contiguous along B) ---------------------
+        // Passes walk the B groups first, so one warp finishes a whole TB*ES-byte output run per A row
+        // in NBG consecutive instructions.
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int a_l = 4 * (w + 8 * (p % PA)) + a_lo;
-            const int bq = bq_lo + 8 * (p / PA);
+        for (int p = 0; p < NP; ++p) {
+            const int a_l = 4 * (w + 8 * (p / NBG)) + a_lo;
+            const int bq = bq_lo + 8 * (p % NBG);
             uint32_t wds[4];
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
                 const int b_l = bq * CH + i;
-                const int word = b_l * 64 + (((a_l / CH) ^ (bq & 7)) * 4) + (a_l % CH) * EW;
+                const int word = b_l * RW + (((a_l / CH) ^ (bq & 7)) * 4) + (a_l % CH) * EW;
                 if constexpr (ES == 4) wds[i] = smem[word];
                 else { const uint2 t = *reinterpret_cast<const uint2*>(&smem[word]); wds[2 * i] = t.x; wds[2 * i + 1] = t.y; }
             }
             const uint64_t a = a0 + a_l, b = b0 + (uint64_t)bq * CH;
             const int64_t e = out_base + (int64_t)a * T.out_stride_a + (int64_t)b;
             if constexpr (VEC) {
-                if (a < T.len_a && b < T.len_b)
+                if (full || (a < T.len_a && b < T.len_b))
                     asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(out + e * ES), "r"(wds[0]), "r"(wds[1]), "r"(wds[2]), "r"(wds[3]) : "memory");
             } else {
 #pragma unroll
@@ -241,28 +256,41 @@ static bool use_pipe() {
     return on;
 }
 
+template <int ES, int TAC, int TB>
+static void launch_tr(const TransposePlan& T, void* out, int grid, bool vec, cudaStream_t stream) {
+    constexpr int smem = TB * TAC * 16;
+    if (vec) {
+        static const bool once = [] { return cudaFuncSetAttribute(k_transpose<ES, true, TAC, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess; }();
+        (void)once;
+        launch_pdl(k_transpose<ES, true, TAC, TB>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);
+    } else {
+        static const bool once = [] { return cudaFuncSetAttribute(k_transpose<ES, false, TAC, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess; }();
+        (void)once;
+        launch_pdl(k_transpose<ES, false, TAC, TB>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);
+    }
+}
+
+// Tile shapes the planner may ask for (TransposePlan::tile_ac x tile_b).  16 chunks x 64 rows (16 KB, 256-byte runs
+// both ways) is the default; 32 x 128 (64 KB, 512-byte runs) is kept for MDIM_TR_TILE=32x128 experiments — measured
+// equal at 16384^2 (6.31 vs 6.32 TB/s) and slower at 4096^2 (5.25 vs 5.67), as are 32 x 64 and 16 x 128 (5.1 TB/s).
+#define MDIM_TR_SHAPES(X) X(16, 64) X(32, 128)
+
 void launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t stream) {
     const bool vec = transpose_vec_ok(T, out);
-    constexpr int smem = kTrStages * 64 * 64 * 4;
-    if (vec && use_pipe()) {
+    if (vec && use_pipe() && T.tile_ac == 16 && T.tile_b == 64) {
+        constexpr int smem = kTrStages * 64 * 64 * 4;
         if (T.esize == 4) launch_pdl(k_transpose_pipe<4>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);
         else launch_pdl(k_transpose_pipe<8>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);
         return;
     }
-    if (T.esize == 4) {
-        if (vec) launch_pdl(k_transpose<4, true>, dim3(grid), dim3(kTrThreads), 0, stream, T, out);
-        else launch_pdl(k_transpose<4, false>, dim3(grid), dim3(kTrThreads), 0, stream, T, out);
-    } else {
-        if (vec) launch_pdl(k_transpose<8, true>, dim3(grid), dim3(kTrThreads), 0, stream, T, out);
-        else launch_pdl(k_transpose<8, false>, dim3(grid), dim3(kTrThreads), 0, stream, T, out);
+#define X(AC, B)                                                                      \
+    if (T.tile_ac == AC && T.tile_b == B) {                                           \
+        if (T.esize == 4) launch_tr<4, AC, B>(T, out, grid, vec, stream);             \
+        else launch_tr<8, AC, B>(T, out, grid, vec, stream);                          \
+        return;                                                                       \
     }
-}
-
-int transpose_max_ctas_per_sm() {
-    int n = 0;
-    if (use_pipe()) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_transpose_pipe<4>, kTrThreads, kTrStages * 64 * 64 * 4);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_transpose<4, true>, kTrThreads, 0);
-    return n > 0 ? n : 1;
+    MDIM_TR_SHAPES(X)
+#undef X
 }
 
 }  // namespace mdim

@@ -47,7 +47,6 @@ const EvalVariant* eval_variants_s64_static(int* n);
 // ------------------------------------------------------------------------------------------------
 constexpr int kTrThreads = 256;
 void launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t stream);
-int transpose_max_ctas_per_sm();
 
 // ------------------------------------------------------------------------------------------------
 // K4: sequential-order last-axis fold, optionally fused with a broadcast epilogue (k_fold.cu)

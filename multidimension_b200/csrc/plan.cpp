@@ -561,13 +561,19 @@ int Builder::detect_fast_paths() {
                 T.batch_out_stride[T.n_batch] = ostride[g];
                 T.n_batch++;
             }
-            const uint64_t tile_a = 256 / (uint64_t)es;  // 16 chunks of 16 bytes along A (k_transpose: TA)
-            T.tiles_a = (T.len_a + tile_a - 1) / tile_a; T.tiles_b = (T.len_b + 63) / 64;
+            // tile shape: MDIM_TR_TILE="<chunks along A>x<rows>" overrides the default (see k_transpose.cu)
+            T.tile_ac = 16; T.tile_b = 64;
+            if (const char* ts = getenv("MDIM_TR_TILE")) {
+                int ac = 0, tb = 0;
+                if (sscanf(ts, "%dx%d", &ac, &tb) == 2 && ((ac == 16 && tb == 64) || (ac == 32 && tb == 128))) { T.tile_ac = ac; T.tile_b = tb; }
+            }
+            const uint64_t tile_a = (uint64_t)T.tile_ac * 16 / (uint64_t)es;
+            T.tiles_a = (T.len_a + tile_a - 1) / tile_a; T.tiles_b = (T.len_b + T.tile_b - 1) / T.tile_b;
             uint64_t nb = 1; for (int b = 0; b < T.n_batch; ++b) nb *= T.batch_len[b];
             T.n_tiles = T.tiles_a * T.tiles_b * nb;
             { const char* ord = getenv("MDIM_TR_ORDER"); T.a_fastest = ord ? atoi(ord) : 0; }
             plan->kind = KK_TRANSPOSE;
-            snprintf(plan->describe, sizeof plan->describe, "transpose.tile64 es%d a=%llu b=%llu batch=%llu", es,
+            snprintf(plan->describe, sizeof plan->describe, "transpose.tile%dx%d es%d a=%llu b=%llu batch=%llu", (int)tile_a, T.tile_b, es,
                      (unsigned long long)T.len_a, (unsigned long long)T.len_b, (unsigned long long)nb);
             return MDIM_OK;
         }

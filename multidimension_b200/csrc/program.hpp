@@ -135,6 +135,7 @@ struct TransposePlan {
     int64_t src_stride_b;        // source stride along B (A has source stride 1)
     int64_t out_stride_a;        // out stride along A (B has out stride 1)
     uint64_t tiles_a, tiles_b, n_tiles;
+    int32_t tile_ac, tile_b;     // tile shape: 16-byte chunks along A (source run = 16*tile_ac bytes) x source rows
     int32_t a_fastest;           // tile order: 1 = consecutive tiles advance along A (source-contiguous) first
 };
 

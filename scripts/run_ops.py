@@ -70,6 +70,27 @@ if "c1" in ops:
     run("c1", dev((usize, usize), (m, m), big[: m * m], "f32").transpose((), usize, usize, ()), out(tout[: m * m]), 8 * m * m)
     m = 16384
     run("c1_16k", dev((usize, usize), (m, m), big[: m * m], "f32").transpose((), usize, usize, ()), out(tout[: m * m]), 8 * m * m)
+if "c1rot" in ops and args.reps:
+    # 4096^2 on 16 rotating buffer pairs (2 GiB touched per round, > L2), the way bench.py times config 1
+    m = 4096
+    preps = [dev((usize, usize), (m, m), big[k * m * m: (k + 1) * m * m], "f32").transpose((), usize, usize, ())
+             .prepare(out=out(tout[k * m * m: (k + 1) * m * m]), flags=args.flags | F.COLLECT_ASYNC) for k in range(16)]
+    for p_ in preps:
+        p_.run()
+    ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for r in range(args.reps):
+        for p_ in preps:
+            p_.run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (16 * args.reps)
+    print(f"  c1rot: {ms:.4f} ms  {8 * m * m / ms / 1e6:.1f} GB/s", flush=True)
+if "c1f64" in ops:
+    m = 8192
+    run("c1f64", dev((usize, usize), (m, m), big.view(torch.float64)[: m * m], "f64").transpose((), usize, usize, ()),
+        out(tout.view(torch.float64)[: m * m], F.F64), 16 * m * m)
 if "c3" in ops:
     n3 = 1 << 28
     tidx = torch.randint(0, n, (n3,), device="cuda", dtype=torch.int64)

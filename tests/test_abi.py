@@ -49,7 +49,7 @@ def test_planner_picks_the_intended_kernels():
     assert "SigMulAddCF32 r1" in a.zip(b).map(lambda p: p[0] * p[1] + np.float32(1)).describe()
     assert "SigMulAddCF32 r1" in (a * b + Scalar(1.0, "f32")).describe()
     m = Array.new((usize, usize), (128, 256), f(128, 256))
-    assert m.transpose((), usize, usize, ()).describe().startswith("transpose.tile64")
+    assert m.transpose((), usize, usize, ()).describe().startswith("transpose.tile")
     idx = Array.new(usize, 64, rng.integers(0, 1 << 12, 64).astype(np.uint64))
     assert "SigGatherF32" in idx.compose(a).describe()
     c = Array.new((usize, usize, usize), (4, 8, 64), f(4, 8, 64))
