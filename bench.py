@@ -503,8 +503,38 @@ def bench_multi_ops(ctx, torch, dist, rank, world, ta, tout, dev_array, out_stor
     ms, _ = time_launches(ag_then_gather, 5, 3)
     out["compose_sharded_source_allgather"] = {"GB/s": round(alg / (ms * 1e-3) / 1e9, 1), "ms": round(ms, 4),
                                                "note": "ncclAllGather of the 4 GiB source + local gather"}
+    del full, tidx
+    # (e) transpose of a ROW-SHARDED source, every rank collecting its block of the transposed rows (SURVEY.md §8e,
+    #     transpose row): the all-to-all is fused into the tiled transpose kernel — each tile is loaded from the
+    #     owning peer's HBM over NVLink — vs NCCL all-gather of the source + a local transpose.
+    M = 16384
+    tblock = M * M // world                         # this rank's rows: the first M*M/world elements of its `ta`
+    tpeers = sharding.PeerStorage(F.F32, M * M, peers.peers, tblock, keep=src_block, ctx=ctx)
+    vt = sharding.shard_view(Array((usize, usize), (M, M), tpeers, "f32").transpose((), usize, usize, ()), rank, world)
+    ot = out_storage(tout[:tblock], F.F32)
+    prep_t = vt.prepare(out=ot, flags=F.COLLECT_ASYNC)
+    prep_t.run()
+    whole = full_buf[: M * M]
+    dist.all_gather_into_tensor(whole, ta[:tblock])
+    lo_t, hi_t = sharding.shard_bounds(M, world, rank)
+    assert torch.equal(tout[:tblock].view(hi_t - lo_t, M), whole.view(M, M).t()[lo_t:hi_t]), "peer-sharded transpose mismatch"
+    ms, _ = time_launches(prep_t.run, 5, 3)
+    out["transpose_sharded_source_peer_mapped"] = {"GB/s": round(8 * M * M / (ms * 1e-3) / 1e9, 1), "ms": round(ms, 4), "kernel": vt.describe(),
+                                                   "note": f"{M}x{M} f32 sharded by rows; each tile is read from the owning peer over NVLink; no collective"}
+    vt2 = sharding.shard_view(dev_array((usize, usize), (M, M), whole, "f32").transpose((), usize, usize, ()), rank, world)
+    prep_t2 = vt2.prepare(out=ot, flags=F.COLLECT_ASYNC)
+
+    def ag_then_transpose():
+        dist.all_gather_into_tensor(whole, ta[:tblock])
+        prep_t2.run()
+    ag_then_transpose()
+    torch.cuda.synchronize()
+    assert torch.equal(tout[:tblock].view(hi_t - lo_t, M), whole.view(M, M).t()[lo_t:hi_t]), "all-gather + transpose mismatch"
+    ms, _ = time_launches(ag_then_transpose, 5, 3)
+    out["transpose_sharded_source_allgather"] = {"GB/s": round(8 * M * M / (ms * 1e-3) / 1e9, 1), "ms": round(ms, 4),
+                                                 "note": "ncclAllGather of the 1 GiB source + local transpose of this rank's block"}
     peers.close()
-    del full, full_buf, tidx
+    del full_buf, whole
     # (d) BASELINE config 5 — the rank-5 transpose -> diagonal -> broadcast -> map chain, 2^30 outputs — sharded
     #     over the ranks along its outermost index (strong scaling: every rank writes 2^30 / world elements)
     Pn = Qn = Rn = 64

@@ -126,9 +126,11 @@ typedef struct mdim_node {
     int32_t op;        /* BINARY: mdim_binary_op; UNARY: mdim_unary_op; FOLD: mdim_binary_op */
     int32_t n_comp;    /* GATHER: number of index components (= children); DIAG: number of pairs */
     int32_t src_dtype; /* UNARY/CAST: dtype of the operand */
-    int32_t n_peers;   /* GATHER: 0/1 = `data` is one buffer; k>1 = source is split into k equal
-                          blocks of `peer_block` elements along its linear index, block p at
-                          peer[p] (peer-mapped HBM of the other GPUs of the box, read over NVLink) */
+    int32_t n_peers;   /* LEAF/GATHER: 0/1 = `data` is one buffer; k>1 = the source Array is split into k
+                          equal blocks of `peer_block` elements along its linear index, block p at
+                          peer[p] (peer-mapped HBM of the other GPUs of the box, read over NVLink).
+                          A sharded LEAF is what a transpose of a row-sharded Array reads: the all-to-all
+                          happens inside the transpose kernel, tile by tile */
     const void* data;  /* LEAF/GATHER: device base pointer of the source Array's items */
     int64_t offset;    /* LEAF/GATHER/IOTA: constant element offset (Row/Column/fixed coords) */
     int64_t stride[MDIM_MAX_RANK];  /* LEAF/GATHER/IOTA: elements per step of each iteration axis;

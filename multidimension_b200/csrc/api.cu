@@ -660,7 +660,7 @@ extern "C" int mdim_collect_host(mdim_ctx* ctx, const mdim_expr* e, void* out_ho
             continue;
         }
         if (n.kind != MDIM_NODE_LEAF && n.kind != MDIM_NODE_GATHER) continue;
-        if (n.kind == MDIM_NODE_GATHER && n.n_peers > 1) return set_error(ctx, MDIM_ERR_INVALID, "peer-sharded gather source in a host collect");
+        if (n.n_peers > 1) return set_error(ctx, MDIM_ERR_INVALID, "peer-sharded source in a host collect");
         const NodeRange all = node_reach(e, n, ranges[i], 0);
         int b = -1;
         for (size_t k = 0; k < bufs.size(); ++k) if (bufs[k].base == (const char*)n.data) b = (int)k;

@@ -26,8 +26,23 @@ namespace mdim {
 
 constexpr int tr_min_ctas(int smem_bytes) { return 227 * 1024 / (smem_bytes + 1024) > 8 ? 8 : 227 * 1024 / (smem_bytes + 1024); }
 
-template <int ES, bool VEC, int TAC, int TB>
-__global__ void __launch_bounds__(kTrThreads, tr_min_ctas(TB * TAC * 16)) k_transpose(const __grid_constant__ TransposePlan T, void* __restrict__ out_v) {
+// Address of element `e` of the source.  PEER: the Array is cut into equal blocks of peer_block elements, block p in
+// the HBM of GPU p (mapped into this process with CUDA IPC); the owner is e / peer_block, estimated in f32 and
+// corrected exactly (e < 2^31 on this path, at most 8 peers, so the estimate is off by at most one).
+template <bool PEER, int ES>
+__device__ __forceinline__ const char* tr_src(const TransposePlan& T, int64_t e) {
+    if constexpr (!PEER) return (const char*)T.src + e * ES;
+    else {
+        int p = (int)((float)e * T.peer_inv);
+        p = p >= T.n_peers ? T.n_peers - 1 : p;
+        if ((int64_t)((uint64_t)p * T.peer_block) > e) --p;
+        else if ((int64_t)((uint64_t)(p + 1) * T.peer_block) <= e) ++p;
+        return (const char*)T.peer[p] + (e - (int64_t)((uint64_t)p * T.peer_block)) * ES;
+    }
+}
+
+template <int ES, bool VEC, int TAC, int TB, bool PEER>
+__global__ void __launch_bounds__(kTrThreads, PEER && tr_min_ctas(TB * TAC * 16) > 6 ? 6 : tr_min_ctas(TB * TAC * 16)) k_transpose(const __grid_constant__ TransposePlan T, void* __restrict__ out_v) {
     constexpr int CH = 16 / ES;            // elements per 16-byte chunk
     constexpr int EW = ES / 4;             // 32-bit words per element
     constexpr int TA = TAC * CH;           // tile extent along A (elements); TAC chunks = TAC*16 bytes per source run
@@ -41,7 +56,6 @@ __global__ void __launch_bounds__(kTrThreads, tr_min_ctas(TB * TAC * 16)) k_tran
     extern __shared__ __align__(16) uint32_t smem[];  // TB x RW words
     pdl_entry();
 
-    const char* __restrict__ src = (const char*)T.src;
     char* __restrict__ out = (char*)out_v;
     const int tid = threadIdx.x;
     // load-phase coordinates
@@ -89,14 +103,14 @@ __global__ void __launch_bounds__(kTrThreads, tr_min_ctas(TB * TAC * 16)) k_tran
                 if constexpr (VEC) {
                     if (full || (b < T.len_b && a < T.len_a))
                         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                     : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w) : "l"(src + e * ES));
+                                     : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w) : "l"(tr_src<PEER, ES>(T, e)));
                 } else {
                     uint32_t wds[4] = {0, 0, 0, 0};
 #pragma unroll
                     for (int i = 0; i < CH; ++i) {
                         if (b < T.len_b && a + i < T.len_a) {
-                            if constexpr (ES == 4) wds[i] = __ldg((const uint32_t*)(src + (e + i) * 4));
-                            else { const uint2 t = __ldg((const uint2*)(src + (e + i) * 8)); wds[2 * i] = t.x; wds[2 * i + 1] = t.y; }
+                            if constexpr (ES == 4) wds[i] = __ldg((const uint32_t*)tr_src<PEER, ES>(T, e + i));
+                            else { const uint2 t = __ldg((const uint2*)tr_src<PEER, ES>(T, e + i)); wds[2 * i] = t.x; wds[2 * i + 1] = t.y; }
                         }
                     }
                     v[q] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
@@ -246,6 +260,10 @@ static bool transpose_vec_ok(const TransposePlan& T, const void* out) {
     bool vec = ((uintptr_t)T.src + (uintptr_t)(T.src_offset * T.esize)) % 16 == 0 && ((uintptr_t)out % 16) == 0 && T.src_stride_b % ch == 0 &&
                T.out_stride_a % ch == 0 && T.len_a % ch == 0 && T.len_b % ch == 0;
     for (int k = 0; k < T.n_batch; ++k) vec = vec && T.batch_src_stride[k] % ch == 0 && T.batch_out_stride[k] % ch == 0;
+    if (T.n_peers > 1) {  // every 16-byte chunk must lie inside one peer's block, 16-byte aligned there
+        vec = vec && T.peer_block % ch == 0 && T.src_offset % ch == 0;
+        for (int p = 0; p < T.n_peers; ++p) vec = vec && ((uintptr_t)T.peer[p] % 16) == 0;
+    }
     return vec;
 }
 
@@ -256,18 +274,19 @@ static bool use_pipe() {
     return on;
 }
 
+template <int ES, bool VEC, int TAC, int TB, bool PEER>
+static void launch_tr1(const TransposePlan& T, void* out, int grid, cudaStream_t stream) {
+    constexpr int smem = TB * TAC * 16;
+    static const bool once = [] { return cudaFuncSetAttribute(k_transpose<ES, VEC, TAC, TB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess; }();
+    (void)once;
+    launch_pdl(k_transpose<ES, VEC, TAC, TB, PEER>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);
+}
+
 template <int ES, int TAC, int TB>
 static void launch_tr(const TransposePlan& T, void* out, int grid, bool vec, cudaStream_t stream) {
-    constexpr int smem = TB * TAC * 16;
-    if (vec) {
-        static const bool once = [] { return cudaFuncSetAttribute(k_transpose<ES, true, TAC, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess; }();
-        (void)once;
-        launch_pdl(k_transpose<ES, true, TAC, TB>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);
-    } else {
-        static const bool once = [] { return cudaFuncSetAttribute(k_transpose<ES, false, TAC, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess; }();
-        (void)once;
-        launch_pdl(k_transpose<ES, false, TAC, TB>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);
-    }
+    const bool peer = T.n_peers > 1;
+    if (vec) { if (peer) launch_tr1<ES, true, TAC, TB, true>(T, out, grid, stream); else launch_tr1<ES, true, TAC, TB, false>(T, out, grid, stream); }
+    else { if (peer) launch_tr1<ES, false, TAC, TB, true>(T, out, grid, stream); else launch_tr1<ES, false, TAC, TB, false>(T, out, grid, stream); }
 }
 
 // Tile shapes the planner may ask for (TransposePlan::tile_ac x tile_b).  16 chunks x 64 rows (16 KB, 256-byte runs
@@ -277,7 +296,7 @@ static void launch_tr(const TransposePlan& T, void* out, int grid, bool vec, cud
 
 void launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t stream) {
     const bool vec = transpose_vec_ok(T, out);
-    if (vec && use_pipe() && T.tile_ac == 16 && T.tile_b == 64) {
+    if (vec && use_pipe() && T.tile_ac == 16 && T.tile_b == 64 && T.n_peers <= 1) {
         constexpr int smem = kTrStages * 64 * 64 * 4;
         if (T.esize == 4) launch_pdl(k_transpose_pipe<4>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);
         else launch_pdl(k_transpose_pipe<8>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);

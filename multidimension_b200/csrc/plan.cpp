@@ -117,7 +117,10 @@ int Builder::validate() {
         for (int c = 0; c < k; ++c) has_err_source[i] = has_err_source[i] || has_err_source[child[i][c]];
         switch (n.kind) {
             case MDIM_NODE_LEAF:
-                if (!n.data) return why.fail(MDIM_ERR_INVALID, "node %d: null data", i);
+                if (n.n_peers > 1) {
+                    if (n.n_peers > MDIM_MAX_PEERS || n.peer_block == 0) return why.fail(MDIM_ERR_INVALID, "node %d: bad peer table", i);
+                    for (int p = 0; p < n.n_peers; ++p) if (!n.peer[p]) return why.fail(MDIM_ERR_INVALID, "node %d: null peer %d", i, p);
+                } else if (!n.data) return why.fail(MDIM_ERR_INVALID, "node %d: null data", i);
                 break;
             case MDIM_NODE_GATHER:
                 if (n.n_peers > 1) {
@@ -280,6 +283,25 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
     const int V = P.vec;
     switch (n.kind) {
         case MDIM_NODE_LEAF: {
+            if (n.n_peers > 1) {
+                // A sharded Array outside the transpose fast path: IOTA of its linear index, then the gather
+                // path's peer lookup (scalar loads; consecutive lanes still read consecutive elements).
+                int islot; int st = new_addr(&islot); if (st) return st;
+                P.addr[islot].ptr = nullptr;
+                Instr io; memset(&io, 0, sizeof io);
+                io.opc = OPC_IOTA; io.dtype = MDIM_U64; io.slot = (uint16_t)islot;
+                st = push_instr(io); if (st) return st;
+                if (P.n_addr >= kMaxAddr) return why.fail(MDIM_ERR_UNSUPPORTED, "too many array operands (> %d)", kMaxAddr);
+                if (P.peers.block != 0) return why.fail(MDIM_ERR_UNSUPPORTED, "more than one peer-sharded source");
+                const int gslot = P.n_addr++;
+                Addr& G = P.addr[gslot];
+                memset(&G, 0, sizeof G);
+                G.ptr = n.peer[0]; G.gstride[0] = 1; G.bound[0] = (uint64_t)n.n_peers * n.peer_block; G.n_peers = n.n_peers;
+                for (int p = 0; p < n.n_peers; ++p) P.peers.peer[p] = n.peer[p];
+                P.peers.block = n.peer_block;
+                in.opc = OPC_GATHER; in.slot = (uint16_t)gslot; in.aux = 1; in.n = (uint16_t)ni;
+                return push_instr(in);
+            }
             int slot; int st = new_addr(&slot); if (st) return st;
             const Addr& A = P.addr[slot];
             const int es = dtype_size(n.dtype);
@@ -454,6 +476,7 @@ int Builder::emit() {
         if (dtype_size(e->nodes[i].dtype) == 8) slot = 8;
         if (e->nodes[i].kind == MDIM_NODE_UNARY && e->nodes[i].op == MDIM_CAST && dtype_size(e->nodes[i].src_dtype) == 8) slot = 8;
         if (e->nodes[i].kind == MDIM_NODE_IOTA && dtype_size(e->nodes[i].dtype) == 8) slot = 8;
+        if (e->nodes[i].kind == MDIM_NODE_LEAF && e->nodes[i].n_peers > 1) slot = 8;  // read as a gather of its own linear index
     }
     plan->slot_bytes = slot;
     // vector width along the innermost output axis
@@ -547,7 +570,11 @@ int Builder::detect_fast_paths() {
         if ((es == 4 || es == 8) && axis_a >= 0 && s[axis_b] != 1 && s[axis_b] != 0 && len[axis_a] >= 16 && len[axis_b] >= 16 && !plan->wide) {
             TransposePlan& T = plan->tr;
             memset(&T, 0, sizeof T);
-            T.src = N[0].data; T.esize = es; T.src_offset = N[0].offset;
+            T.src = N[0].n_peers > 1 ? N[0].peer[0] : N[0].data; T.esize = es; T.src_offset = N[0].offset;
+            if (N[0].n_peers > 1) {
+                T.n_peers = N[0].n_peers; T.peer_block = N[0].peer_block; T.peer_inv = 1.0f / (float)N[0].peer_block;
+                for (int p = 0; p < N[0].n_peers; ++p) T.peer[p] = N[0].peer[p];
+            }
             T.len_a = len[axis_a]; T.len_b = len[axis_b];
             T.src_stride_b = s[axis_b];
             // out strides: row-major over canonical out axes
@@ -573,7 +600,7 @@ int Builder::detect_fast_paths() {
             T.n_tiles = T.tiles_a * T.tiles_b * nb;
             { const char* ord = getenv("MDIM_TR_ORDER"); T.a_fastest = ord ? atoi(ord) : 0; }
             plan->kind = KK_TRANSPOSE;
-            snprintf(plan->describe, sizeof plan->describe, "transpose.tile%dx%d es%d a=%llu b=%llu batch=%llu", (int)tile_a, T.tile_b, es,
+            snprintf(plan->describe, sizeof plan->describe, "transpose.tile%dx%d%s es%d a=%llu b=%llu batch=%llu", (int)tile_a, T.tile_b, T.n_peers > 1 ? ".peers" : "", es,
                      (unsigned long long)T.len_a, (unsigned long long)T.len_b, (unsigned long long)nb);
             return MDIM_OK;
         }
@@ -587,7 +614,7 @@ int Builder::detect_fast_paths() {
         const int es = dtype_size(F.dtype);
         auto rows_leaf = [&](int ni, bool with_red, int out_rank_expected) -> bool {
             // contiguous (rows, row_len) leaf: red stride 1 (if with_red) and row stride row_len
-            if (N[ni].kind != MDIM_NODE_LEAF || N[ni].dtype != F.dtype) return false;
+            if (N[ni].kind != MDIM_NODE_LEAF || N[ni].dtype != F.dtype || N[ni].n_peers > 1) return false;
             const int64_t* s = cstride[ni];
             (void)out_rank_expected;
             if (with_red && s[n_axes - 1] != 1) return false;

@@ -137,6 +137,13 @@ struct TransposePlan {
     uint64_t tiles_a, tiles_b, n_tiles;
     int32_t tile_ac, tile_b;     // tile shape: 16-byte chunks along A (source run = 16*tile_ac bytes) x source rows
     int32_t a_fastest;           // tile order: 1 = consecutive tiles advance along A (source-contiguous) first
+    // Source sharded over peer GPUs (mdim_node.n_peers on the LEAF): element e of the whole Array lives at
+    // peer[e / peer_block] + (e % peer_block).  The kernel reads the owning peer's HBM over NVLink, so the
+    // all-to-all a row-sharded transpose implies happens inside the tile loads.
+    int32_t n_peers;
+    float peer_inv;              // 1 / peer_block (quotient estimate, corrected exactly in the kernel)
+    uint64_t peer_block;
+    const void* peer[MDIM_MAX_PEERS];
 };
 
 struct FoldRowsPlan {

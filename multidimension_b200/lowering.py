@@ -237,8 +237,6 @@ def emit(root, axes, location):
                 if a not in pos:
                     raise Unsupported(f"internal: node strides over an axis that is not iterated ({a!r})")
                 d.stride[pos[a]] = s
-        if n.kind == F.LEAF and n.peers:
-            raise Unsupported("a peer-sharded Array can only be read through compose()/map_axis()")
         if n.kind in (F.LEAF, F.GATHER):
             if n.peers:
                 d.n_peers = len(n.peers)

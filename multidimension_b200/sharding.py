@@ -4,10 +4,11 @@ Elementwise / broadcast / diagonal / transpose-with-replicated-source / non-shar
 nothing from here beyond `shard_bounds`: every rank collects its own block, no data-path collective.
 The two ops with a real exchange step are
 
-  * `compose()` onto a source that is itself sharded: `PeerSource` maps every rank's block into every
-    other rank's address space (CUDA IPC over NVLink/NVSwitch) and the gather kernel reads the owning
-    peer's HBM directly (`mdim_node.n_peers`); `all_gather_source` is the NCCL alternative the north
-    star names (it moves the whole source first);
+  * `compose()` onto, or a `transpose()` of, a source that is itself sharded: `peer_source` maps every
+    rank's block into every other rank's address space (CUDA IPC over NVLink/NVSwitch) and the gather /
+    transpose kernel reads the owning peer's HBM directly (`mdim_node.n_peers`), so the exchange is fused
+    into the kernel; `all_gather_source` is the NCCL alternative the north star names (it moves the whole
+    source first);
   * a fold over the sharded axis itself: every rank folds its block, then `all_reduce_partial`
     (NCCL all-reduce; f32 order differs from the sequential reference, 1e-6 relative tolerance).
 
@@ -74,7 +75,9 @@ def shard_view(view, rank, world):
 
 class PeerStorage(Storage):
     """A source Array split into `world` equal blocks of `block` elements, block p living on rank p.
-    Only gathers (`compose`, `map_axis`) can read it; the kernel picks the peer per element."""
+    Any view can read it: a transpose goes through the tiled kernel, which fetches each tile from the owning
+    peer (the all-to-all of a row-sharded transpose, fused into the kernel); gathers (`compose`, `map_axis`)
+    and every other chain pick the peer per element."""
 
     def __init__(self, dtype, n, peers, block, keep=None, ctx=None, opened=()):
         super().__init__(dtype, n, dptr=peers[0], ctx=ctx, owns_device=False, keep=keep)

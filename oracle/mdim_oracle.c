@@ -290,6 +290,10 @@ static mdim_scalar at(oracle_t* o, int ni) {
     if (o->failed) return r;
     switch (n->kind) {
         case MDIM_NODE_LEAF: /* src/array.rs:81,86: items[index.to_usize(size)].clone() */
+            if (n->n_peers > 1) { /* the Array's items are split into equal blocks, block p at peer[p] */
+                uint64_t idx = (uint64_t)linear(o, n), p = idx / n->peer_block;
+                return load(n->peer[p], (int64_t)(idx % n->peer_block), n->dtype);
+            }
             return load(n->data, linear(o, n), n->dtype);
         case MDIM_NODE_IOTA: /* src/index.rs:185: at(index) = index */
             r.u64 = (uint64_t)linear(o, n);
@@ -392,8 +396,12 @@ static int validate(oracle_t* o) {
         for (int c = 0; c < k; ++c) o->child[i][c] = stack[sp - k + c];
         sp -= k;
         stack[sp++] = i;
-        if ((n->kind == MDIM_NODE_LEAF || (n->kind == MDIM_NODE_GATHER && n->n_peers <= 1)) && !n->data)
+        if ((n->kind == MDIM_NODE_LEAF || n->kind == MDIM_NODE_GATHER) && n->n_peers <= 1 && !n->data)
             return MDIM_ERR_INVALID;
+        if ((n->kind == MDIM_NODE_LEAF || n->kind == MDIM_NODE_GATHER) && n->n_peers > 1) {
+            if (n->n_peers > MDIM_MAX_PEERS || n->peer_block == 0) return MDIM_ERR_INVALID;
+            for (int q = 0; q < n->n_peers; ++q) if (!n->peer[q]) return MDIM_ERR_INVALID;
+        }
         if (n->kind == MDIM_NODE_BINARY) {
             int l = e->nodes[o->child[i][0]].dtype, r = e->nodes[o->child[i][1]].dtype;
             if (l != n->dtype) return MDIM_ERR_INVALID;

@@ -10,7 +10,7 @@ from helpers import oracle_collect, emu_collect, assert_same_bits
 import multidimension_b200 as P
 from multidimension_b200 import usize, Array, Scalar, Add, fold_rows, _ffi as F
 from multidimension_b200.runtime import Storage
-from multidimension_b200.sharding import shard_bounds, equal_block, PeerStorage
+from multidimension_b200.sharding import shard_bounds, shard_view, equal_block, PeerStorage
 
 
 def test_shard_bounds_partition():
@@ -44,8 +44,63 @@ def test_peer_sharded_compose_matches_replicated(world):
     want = oracle_collect(replicated)
     assert_same_bits(oracle_collect(sharded), want)
     assert_same_bits(emu_collect(sharded), want)
-    with pytest.raises(P.Unsupported):  # a sharded Array is only readable through a gather
-        oracle_collect(Array(usize, src.size, peers, "f32") * Scalar(2.0, "f32"))
+    # ... and a sharded Array is readable by any other chain as well (element-wise peer lookup)
+    want2 = oracle_collect(Array.new(usize, src.size, src) * Scalar(2.0, "f32"))
+    assert_same_bits(oracle_collect(Array(usize, src.size, peers, "f32") * Scalar(2.0, "f32")), want2)
+    assert_same_bits(emu_collect(Array(usize, src.size, peers, "f32") * Scalar(2.0, "f32")), want2)
+
+
+def _sharded_matrix(rng, rows, cols, world, T="f32"):
+    """A (rows, cols) matrix cut into `world` equal blocks of its flat storage (the last block padded)."""
+    dt = {"f32": np.float32, "f64": np.float64}[T]
+    full = rng.uniform(-1, 1, rows * cols).astype(dt)
+    block = equal_block(full.size, world)
+    padded = np.zeros(block * world, dt)
+    padded[:full.size] = full
+    shards = [np.ascontiguousarray(padded[p * block:(p + 1) * block]) for p in range(world)]
+    return full, shards, block
+
+
+@pytest.mark.parametrize("world,shape", [(2, (64, 48)), (3, (50, 36)), (8, (128, 64))])
+def test_peer_sharded_transpose_matches_replicated(world, shape):
+    """SURVEY.md §8e transpose row: source sharded on its outermost axis, every rank collects a column block of
+    the transpose.  The exchange is the kernel's own loads from the owning peer (here: host arrays)."""
+    rng = np.random.default_rng(world * 100 + shape[0])
+    full, shards, block = _sharded_matrix(rng, shape[0], shape[1], world)
+    peers = PeerStorage(F.F32, full.size, [s.ctypes.data for s in shards], block, keep=shards)
+    sharded = Array((usize, usize), shape, peers, "f32").transpose((), usize, usize, ())
+    want = full.reshape(shape).T.copy().reshape(-1)
+    assert_same_bits(oracle_collect(sharded), want)
+    assert_same_bits(emu_collect(sharded), want)
+    for rank in range(world):  # each rank's block of the output (outermost axis of the transpose = columns)
+        lo, hi = shard_bounds(shape[1], world, rank)
+        blockview = shard_view(sharded, rank, world)
+        assert_same_bits(oracle_collect(blockview), full.reshape(shape).T[lo:hi].copy().reshape(-1))
+        assert_same_bits(emu_collect(blockview), full.reshape(shape).T[lo:hi].copy().reshape(-1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,world,shape", [("f32", 2, (256, 192)), ("f32", 3, (250, 131)), ("f64", 8, (512, 320)), ("f32", 8, (1024, 1024))])
+def test_peer_sharded_transpose_gpu(T, world, shape):
+    ctx = P.Context(0)
+    rng = np.random.default_rng(world * 1000 + shape[1])
+    full, shards, block = _sharded_matrix(rng, shape[0], shape[1], world, T)
+    dt = F.F32 if T == "f32" else F.F64
+    dev = [Storage.from_host(dt, s).ensure_device(ctx) for s in shards]
+    peers = PeerStorage(dt, full.size, [d.dptr for d in dev], block, keep=dev, ctx=ctx)
+    sharded = Array((usize, usize), shape, peers, T).transpose((), usize, usize, ())
+    assert ".peers" in sharded.describe()
+    want = full.reshape(shape).T
+    for rank in (0, world - 1):
+        lo, hi = shard_bounds(shape[1], world, rank)
+        got = shard_view(sharded, rank, world).collect(location="device", ctx=ctx).as_ref()
+        assert_same_bits(got, want[lo:hi].copy().reshape(-1))
+    assert_same_bits(sharded.collect(location="device", ctx=ctx).as_ref(), want.copy().reshape(-1))
+    # the same Array through the general evaluator (per-element peer lookup)
+    assert_same_bits(sharded.collect(location="device", ctx=ctx, flags=F.COLLECT_NO_FASTPATH).as_ref(), want.copy().reshape(-1))
+    chain = Array((usize, usize), shape, peers, T) * Scalar(3.0, T)
+    assert_same_bits(chain.collect(location="device", ctx=ctx).as_ref(), full * (np.float32(3) if T == "f32" else 3.0))
+    ctx.close()
 
 
 @pytest.mark.gpu
