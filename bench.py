@@ -186,7 +186,7 @@ def run_reference(args, rank):
     sec = sum(timed) / len(timed)
     v = nbytes / sec / 1e9
     sample = f"{n} of {N_ELEMS} elements per step (same expression, same generator), single thread pinned to one core"
-    print(json.dumps({
+    emit_line({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample,
@@ -194,11 +194,29 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ---- the B200 arm ------------------------------------------------------------------------------------------------------------
+_json_fd = None
+
+
+def keep_stdout_for_json():
+    """Libraries print to fd 1 (NCCL writes its version banner there): point fd 1 at stderr for the rest of
+    the run and keep the original for the ONE JSON line the driver parses."""
+    global _json_fd
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(obj):
+    sys.stdout.flush()
+    os.write(_json_fd if _json_fd is not None else 1, (json.dumps(obj) + "\n").encode())
+
+
 def main():
+    keep_stdout_for_json()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -355,7 +373,7 @@ def main():
                                   "host_cores_available": os.cpu_count(), "ops": cpu_ops_table()}
 
     if rank == 0:
-        print(json.dumps(result))
+        emit_line(result)
     if world > 1:
         dist.destroy_process_group()
 
