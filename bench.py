@@ -551,7 +551,6 @@ def bench_multi_ops(ctx, torch, dist, rank, world, ta, tout, dev_array, out_stor
     ms, _ = time_launches(ag_then_transpose, 5, 3)
     out["transpose_sharded_source_allgather"] = {"GB/s": round(8 * M * M / (ms * 1e-3) / 1e9, 1), "ms": round(ms, 4),
                                                  "note": "ncclAllGather of the 1 GiB source + local transpose of this rank's block"}
-    peers.close()
     del full_buf, whole
     # (d) BASELINE config 5 — the rank-5 transpose -> diagonal -> broadcast -> map chain, 2^30 outputs — sharded
     #     over the ranks along its outermost index (strong scaling: every rank writes 2^30 / world elements)
@@ -599,6 +598,33 @@ def bench_multi_ops(ctx, torch, dist, rank, world, ta, tout, dev_array, out_stor
     alg = (4 * I * J * K) * world + 4 * J * K
     out["fold_sharded_axis_allreduce"] = {"GB/s": round(alg / (ms * 1e-3) / 1e9, 1), "ms": round(ms, 4), "kernel": part_view.describe(),
                                           "max_rel_err_vs_f64": rel, "note": "per-rank partial fold + ncclAllReduce(sum) of 1 MiB"}
+    # (c') the same fold with NO reassociation: every rank folds ITS block of the (J, K) result over the whole
+    #      sharded axis, reading the peers' blocks in index order -> bit-identical to the unsharded sequential fold.
+    barrier()
+    fpeers = sharding.PeerStorage(F.F32, I * world * J * K, peers.peers, I * J * K, keep=t4, ctx=ctx)
+    whole3 = Array((usize, usize, usize), (I * world, J, K), fpeers, "f32")
+    exact_view = sharding.shard_view(
+        fold_rows(whole3.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize)), (usize, usize), usize, Add, np.float32(0)), rank, world)
+    j_lo, j_hi = sharding.shard_bounds(J, world, rank)
+    texact = torch.empty((j_hi - j_lo) * K, device="cuda", dtype=torch.float32)
+    prep_x = exact_view.prepare(out=out_storage(texact, F.F32), flags=F.COLLECT_ASYNC)
+    prep_x.run()
+    torch.cuda.synchronize()
+    gathered = [torch.empty(I * (j_hi - j_lo) * K, device="cuda", dtype=torch.float32) for _ in range(world)]
+    mine_cols = [t4.view(I, J, K)[:, sharding.shard_bounds(J, world, r)[0]:sharding.shard_bounds(J, world, r)[1], :].contiguous().view(-1) for r in range(world)]
+    for r in range(world):  # rank r receives every rank's rows of ITS column block
+        dist.gather(mine_cols[r], gathered if rank == r else None, dst=r)
+    seq = torch.zeros((j_hi - j_lo) * K, device="cuda", dtype=torch.float32)
+    for blk in gathered:
+        for i in range(I):
+            seq += blk.view(I, -1)[i]
+    assert torch.equal(texact, seq), "peer-mapped fold over the sharded axis is not bit-exact"
+    del gathered, mine_cols
+    ms, _ = time_launches(prep_x.run, 5, 3)
+    out["fold_sharded_axis_peer_mapped_bit_exact"] = {"GB/s": round(alg / (ms * 1e-3) / 1e9, 1), "ms": round(ms, 4), "kernel": exact_view.describe(),
+                                                      "note": "each rank folds its block of the result over ALL ranks' rows in index order (reads over NVLink): "
+                                                              "bit-identical to the sequential reference, no collective"}
+    peers.close()
     return out
 
 

@@ -42,7 +42,7 @@ static bool sig_matches(const EvalVariant& v, const char* sig, int sig_len) {
         if (v.sig[i].opc != s[0] || v.sig[i].dtype != s[1]) return false;
         // op/aux only matter for the opcodes that read them
         const int opc = v.sig[i].opc;
-        if (opc == OPC_LEAF_VEC && v.sig[i].aux != s[3]) return false;
+        if ((opc == OPC_LEAF_VEC || opc == OPC_LEAF_BCAST || opc == OPC_LEAF_STRIDED) && v.sig[i].aux != s[3]) return false;  // aux: bit 0 cached, bit 1 sharded
         if ((opc == OPC_BINARY || opc == OPC_UNARY || opc == OPC_FOLD_STEP) && (v.sig[i].op != s[2] || v.sig[i].aux != s[3])) return false;
         if (opc == OPC_GATHER && v.sig[i].aux != s[3]) return false;
     }

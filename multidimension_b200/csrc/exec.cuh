@@ -584,6 +584,20 @@ template <bool WIDE, int MAXR> MDIM_FN void advance_red(const Program& P, Thread
 // SLOTK >= 0: the address slot is known at compile time (static signatures: slots are handed out in
 // instruction order, so it is the number of addressed instructions before this one).  Reading it from the
 // program instead makes every stride a register-indexed constant load (LDC) rather than a uniform one.
+// A LEAF whose Array is sharded over the GPUs of the box (instruction aux bit 1; mdim_node.n_peers): element `off`
+// of the whole Array lives at peers.peer[off / block] + off % block.  Vectors never straddle two blocks (the
+// planner only vectorises when block boundaries are vector-aligned).
+template <bool WIDE> MDIM_FN const void* leaf_base(const Program& P, int slot, int aux, int64_t& off) {
+    if (aux & 2) {
+        uint64_t p;
+        if constexpr (WIDE) p = (uint64_t)off / P.peers.block;
+        else p = (uint32_t)off / (uint32_t)P.peers.block;  // 32-bit coordinates: every offset is below 2^31
+        off -= (int64_t)(p * P.peers.block);
+        return P.peers.peer[p];
+    }
+    return P.addr[slot].ptr;
+}
+
 template <int D, class S, int V, int MAXD, bool WIDE, int MAXR, int SLOTK = -1>
 MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int op, int aux, int pc,
                        S (&st)[MAXD][V], ThreadState<WIDE, MAXR>& ts) {
@@ -594,21 +608,24 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
     switch (opc) {
         case OPC_LEAF_VEC:  // Array::at = items[to_usize(index)] (src/array.rs:81,86), V at a time
             if constexpr (D < MAXD) {
-                const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, slot, ts);
+                int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, slot, ts);
+                const void* base = leaf_base<WIDE>(P, slot, aux, off);
                 if (ts.mask == (1u << V) - 1u) {  // (a compile-time fact in signatures without MASK)
                     const bool w256 = (P.flags & PF_VEC256) != 0;
-                    if (aux) ld_vector<S, V, true>(P.addr[slot].ptr, off, esize_of(dtype), st[D], w256);   // re-read operand: keep in L1
-                    else ld_vector<S, V, false>(P.addr[slot].ptr, off, esize_of(dtype), st[D], w256);      // read once: stream past L1
+                    if (aux & 1) ld_vector<S, V, true>(base, off, esize_of(dtype), st[D], w256);   // re-read operand: keep in L1
+                    else ld_vector<S, V, false>(base, off, esize_of(dtype), st[D], w256);          // read once: stream past L1
                 } else {  // under a Concat / lazy Diagonal: inactive lanes must not touch memory
                     const int es = esize_of(dtype);
 #pragma unroll
-                    for (int l = 0; l < V; ++l) st[D][l] = ((ts.mask >> l) & 1u) ? ld_scalar<S>(P.addr[slot].ptr, off + l, es) : (S)0;
+                    for (int l = 0; l < V; ++l) st[D][l] = ((ts.mask >> l) & 1u) ? ld_scalar<S>(base, off + l, es) : (S)0;
                 }
             }
             break;
         case OPC_LEAF_BCAST:  // operand lacks the vector axis: Broadcast::index drops it (src/broadcast.rs:46-60)
             if constexpr (D < MAXD) {
-                const S v = ts.mask ? ld_scalar<S>(P.addr[slot].ptr, (int64_t)addr_offset<WIDE, MAXR>(P, slot, ts), esize_of(dtype)) : (S)0;
+                int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, slot, ts);
+                const void* base = leaf_base<WIDE>(P, slot, aux, off);
+                const S v = ts.mask ? ld_scalar<S>(base, off, esize_of(dtype)) : (S)0;
 #pragma unroll
                 for (int l = 0; l < V; ++l) st[D][l] = v;
             }
@@ -618,7 +635,11 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
                 const int64_t off = (int64_t)addr_offset<WIDE, MAXR>(P, slot, ts), s_in = inner_stride(P, slot);
                 const int es = esize_of(dtype);
 #pragma unroll
-                for (int l = 0; l < V; ++l) st[D][l] = ((ts.mask >> l) & 1u) ? ld_scalar<S>(P.addr[slot].ptr, off + (int64_t)l * s_in, es) : (S)0;
+                for (int l = 0; l < V; ++l) {
+                    int64_t o = off + (int64_t)l * s_in;  // (a sharded operand: the lanes may belong to different peers)
+                    const void* base = leaf_base<WIDE>(P, slot, aux, o);
+                    st[D][l] = ((ts.mask >> l) & 1u) ? ld_scalar<S>(base, o, es) : (S)0;
+                }
             }
             break;
         case OPC_IOTA:  // All<I>::at(index) = index (src/index.rs:185)

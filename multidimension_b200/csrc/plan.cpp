@@ -283,47 +283,41 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
     const int V = P.vec;
     switch (n.kind) {
         case MDIM_NODE_LEAF: {
-            if (n.n_peers > 1) {
-                // A sharded Array outside the transpose fast path: IOTA of its linear index, then the gather
-                // path's peer lookup (scalar loads; consecutive lanes still read consecutive elements).
-                int islot; int st = new_addr(&islot); if (st) return st;
-                P.addr[islot].ptr = nullptr;
-                Instr io; memset(&io, 0, sizeof io);
-                io.opc = OPC_IOTA; io.dtype = MDIM_U64; io.slot = (uint16_t)islot;
-                st = push_instr(io); if (st) return st;
-                if (P.n_addr >= kMaxAddr) return why.fail(MDIM_ERR_UNSUPPORTED, "too many array operands (> %d)", kMaxAddr);
+            int slot; int st = new_addr(&slot); if (st) return st;
+            Addr& A = P.addr[slot];
+            const int es = dtype_size(n.dtype);
+            const bool sharded = n.n_peers > 1;  // the Array's items live in equal blocks on the GPUs of the box
+            if (sharded) {
                 if (P.peers.block != 0) return why.fail(MDIM_ERR_UNSUPPORTED, "more than one peer-sharded source");
-                const int gslot = P.n_addr++;
-                Addr& G = P.addr[gslot];
-                memset(&G, 0, sizeof G);
-                G.ptr = n.peer[0]; G.gstride[0] = 1; G.bound[0] = (uint64_t)n.n_peers * n.peer_block; G.n_peers = n.n_peers;
                 for (int p = 0; p < n.n_peers; ++p) P.peers.peer[p] = n.peer[p];
                 P.peers.block = n.peer_block;
-                in.opc = OPC_GATHER; in.slot = (uint16_t)gslot; in.aux = 1; in.n = (uint16_t)ni;
-                return push_instr(in);
+                A.ptr = n.peer[0]; A.n_peers = n.n_peers;
             }
-            int slot; int st = new_addr(&slot); if (st) return st;
-            const Addr& A = P.addr[slot];
-            const int es = dtype_size(n.dtype);
+            // every vector must be `align`-byte aligned wherever it lands: base pointer(s), offset, outer strides
+            // and, for a sharded Array, the block boundaries (so that no vector straddles two peers)
+            auto aligned = [&](int64_t align) {
+                bool ok = (((uintptr_t)A.ptr + (uintptr_t)(A.offset * es)) % align) == 0;
+                for (int g = 0; g < n_axes && ok; ++g)
+                    if (g != rank - 1 && ((cstride[ni][g] * es) % align) != 0) ok = false;
+                if (sharded) {
+                    ok = ok && ((int64_t)(n.peer_block * (uint64_t)es) % align) == 0 && ((A.offset * es) % align) == 0;
+                    for (int p = 0; p < n.n_peers && ok; ++p) ok = ((uintptr_t)n.peer[p] % align) == 0;
+                }
+                return ok;
+            };
             const int64_t s_in = rank > 0 ? cstride[ni][rank - 1] : 0;
             int opc;
             if (rank == 0 || s_in == 0) opc = OPC_LEAF_BCAST;
             else if (s_in == 1) {
-                const int64_t align = std::min<int64_t>(16, (int64_t)V * es);
-                bool ok = (((uintptr_t)A.ptr + (uintptr_t)(A.offset * es)) % align) == 0;
-                for (int g = 0; g < n_axes && ok; ++g)
-                    if (g != rank - 1 && ((cstride[ni][g] * es) % align) != 0) ok = false;
+                bool ok = aligned(std::min<int64_t>(16, (int64_t)V * es));
+                if (sharded && ok) ok = aligned((int64_t)V * es);  // a whole vector inside one block
                 opc = ok ? OPC_LEAF_VEC : OPC_LEAF_STRIDED;
-                if (ok) {  // 256-bit accesses need every vector of this operand 32-byte aligned
-                    bool ok32 = (((uintptr_t)A.ptr + (uintptr_t)(A.offset * es)) % 32) == 0;
-                    for (int g = 0; g < n_axes && ok32; ++g)
-                        if (g != rank - 1 && ((cstride[ni][g] * es) % 32) != 0) ok32 = false;
-                    if (!ok32) plan->vec256_ok = 0;
-                }
+                if (ok && !aligned(32)) plan->vec256_ok = 0;  // 256-bit accesses need every vector of this operand 32-byte aligned
             } else opc = OPC_LEAF_STRIDED;
             in.opc = (uint8_t)opc; in.slot = (uint16_t)slot;
             if (opc == OPC_LEAF_VEC)  // re-read along a broadcast output axis => worth keeping in L1
                 for (int g = 0; g < rank; ++g) if (cstride[ni][g] == 0 && len[g] > 1) in.aux = 1;
+            if (sharded) in.aux |= 2;  // exec.cuh: leaf_base() picks the peer
             return push_instr(in);
         }
         case MDIM_NODE_IOTA: {
@@ -476,7 +470,6 @@ int Builder::emit() {
         if (dtype_size(e->nodes[i].dtype) == 8) slot = 8;
         if (e->nodes[i].kind == MDIM_NODE_UNARY && e->nodes[i].op == MDIM_CAST && dtype_size(e->nodes[i].src_dtype) == 8) slot = 8;
         if (e->nodes[i].kind == MDIM_NODE_IOTA && dtype_size(e->nodes[i].dtype) == 8) slot = 8;
-        if (e->nodes[i].kind == MDIM_NODE_LEAF && e->nodes[i].n_peers > 1) slot = 8;  // read as a gather of its own linear index
     }
     plan->slot_bytes = slot;
     // vector width along the innermost output axis

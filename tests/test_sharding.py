@@ -79,6 +79,54 @@ def test_peer_sharded_transpose_matches_replicated(world, shape):
         assert_same_bits(emu_collect(blockview), full.reshape(shape).T[lo:hi].copy().reshape(-1))
 
 
+def _sharded_axis_fold(arr3, I, J, K):
+    """Fold over the OUTERMOST axis of an (I, J, K) Array in index order: out[j, k] = ((0 + a[0,j,k]) + a[1,j,k]) + ..."""
+    moved = arr3.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize))
+    return fold_rows(moved, (usize, usize), usize, Add, np.float32(0))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fold_over_the_sharded_axis_reading_peers_is_bit_exact(world):
+    """The all-reduce route reassociates the sum (1e-6 tolerance).  Reading the peers' blocks in index order
+    instead keeps the reference's add chain: bit-identical to the unsharded fold."""
+    rng = np.random.default_rng(41 + world)
+    I, J, K = 6 * world, 5, 8
+    full = rng.uniform(0, 1, I * J * K).astype(np.float32)
+    block = equal_block(full.size, world)
+    shards = [np.ascontiguousarray(full[p * block:(p + 1) * block]) for p in range(world)]
+    peers = PeerStorage(F.F32, full.size, [s.ctypes.data for s in shards], block, keep=shards)
+    want = oracle_collect(_sharded_axis_fold(Array.new((usize, usize, usize), (I, J, K), full), I, J, K))
+    view = _sharded_axis_fold(Array((usize, usize, usize), (I, J, K), peers, "f32"), I, J, K)
+    assert_same_bits(oracle_collect(view), want)
+    assert_same_bits(emu_collect(view), want)
+    seq = np.zeros(J * K, np.float32)
+    for i in range(I):
+        seq = seq + full.reshape(I, J * K)[i]
+    assert_same_bits(want, seq)
+
+
+@pytest.mark.gpu
+def test_fold_over_the_sharded_axis_reading_peers_gpu():
+    ctx = P.Context(0)
+    rng = np.random.default_rng(77)
+    world, I, J, K = 4, 64, 48, 32
+    full = rng.uniform(0, 1, I * J * K).astype(np.float32)
+    block = equal_block(full.size, world)
+    shards = [np.ascontiguousarray(full[p * block:(p + 1) * block]) for p in range(world)]
+    dev = [Storage.from_host(F.F32, s).ensure_device(ctx) for s in shards]
+    peers = PeerStorage(F.F32, full.size, [d.dptr for d in dev], block, keep=dev, ctx=ctx)
+    view = _sharded_axis_fold(Array((usize, usize, usize), (I, J, K), peers, "f32"), I, J, K)
+    seq = np.zeros(J * K, np.float32)
+    for i in range(I):
+        seq = seq + full.reshape(I, J * K)[i]
+    assert_same_bits(view.collect(location="device", ctx=ctx).as_ref(), seq)
+    for rank in range(world):  # each rank's block of the (J, K) result
+        lo, hi = shard_bounds(J, world, rank)
+        got = shard_view(view, rank, world).collect(location="device", ctx=ctx).as_ref()
+        assert_same_bits(got, seq.reshape(J, K)[lo:hi].reshape(-1))
+    ctx.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("T,world,shape", [("f32", 2, (256, 192)), ("f32", 3, (250, 131)), ("f64", 8, (512, 320)), ("f32", 8, (1024, 1024))])
 def test_peer_sharded_transpose_gpu(T, world, shape):
