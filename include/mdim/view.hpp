@@ -181,6 +181,14 @@ inline NodeP substitute(const NodeP& n, const Table& t) {
         if (dead) { auto c = std::make_shared<Node>(); c->kind = MDIM_NODE_CONST; c->dtype = n->dtype; c->imm = n->imm; return c; }
         if (ps.empty()) return out->kids[0];
         out->pairs = ps;
+    } else if (n->kind == MDIM_NODE_CONCAT) {  // pairs[0] = {concatenated axis, -, length of V along it}
+        if (const Sub_* sub = lookup(t, n->pairs[0].a)) {
+            const int64_t thr = (int64_t)n->pairs[0].c;
+            if (sub->terms.empty()) return sub->constant < thr ? out->kids[0] : out->kids[1];  // pinned (row/column): one side survives
+            if (sub->terms.size() == 1 && sub->terms[0].second == 1)  // k = k' + c:  k < thr  <=>  k' < thr - c
+                out->pairs[0] = {sub->terms[0].first, nullptr, (uint64_t)std::max<int64_t>(thr - sub->constant, 0)};
+            else throw Unsupported("a Concat whose axis has been split needs device div/mod");
+        }
     } else if (n->kind == MDIM_NODE_FOLD) {
         for (auto& a : n->red_axes) if (lookup(t, a)) throw Unsupported("substitution of a reduction axis");
     }
@@ -229,6 +237,7 @@ inline void emit_and_run(const NodeP& root, const std::vector<AxisP>& axes, cons
         d.kind = n.kind; d.dtype = n.dtype; d.op = n.op; d.src_dtype = n.src_dtype; d.data = n.data; d.offset = n.offset; d.imm = n.imm;
         for (auto& [a, s] : n.stride) d.stride[pos(a)] = s;
         if (n.kind == MDIM_NODE_GATHER) { d.n_comp = (int)n.kids.size(); for (size_t c = 0; c < n.kids.size(); ++c) { d.gstride[c] = n.gstride[c]; d.bound[c] = n.bound[c]; } }
+        if (n.kind == MDIM_NODE_CONCAT) { d.axis_a[0] = pos(n.pairs[0].a); d.axis_c[0] = n.pairs[0].c; }
         if (n.kind == MDIM_NODE_DIAG) {
             d.n_comp = (int)n.pairs.size();
             for (size_t p = 0; p < n.pairs.size(); ++p) { d.axis_a[p] = pos(n.pairs[p].a); if (n.pairs[p].b) d.axis_b[p] = pos(n.pairs[p].b); else { d.axis_b[p] = -1; d.axis_c[p] = n.pairs[p].c; } }
@@ -377,13 +386,114 @@ template <class I, class T> class View {
         Table t; auto ax = flat(gj); for (size_t k = 0; k < ax.size(); ++k) t.push_back({ax[k].get(), pin_at(p[k])});
         return View<I0, T>(std::get<0>(s), gi, substitute(value_, t));
     }
+    // concat::<I, J>(other) (src/view.rs:327-339, 920-946): along the usize axis between I and J; only the
+    // selected side is evaluated (:938-945), W addressed with k - len(V)
+    template <class I0, class J0, class IW> View<std::tuple<I0, usize, J0>, T> concat(const View<IW, T>& other) const {
+        using Mid = std::tuple<I0, usize, J0>;
+        auto sv = to_iso_size<I, Mid>(size_);
+        auto sw = to_iso_size<IW, Mid>(other.size());
+        if (!(std::get<0>(sv) == std::get<0>(sw)) || !(std::get<2>(sv) == std::get<2>(sw)))  // assert_eq!(self_i, other_i) / (self_j, other_j), :336-337
+            throw Panic(MDIM_ERR_SIZE, "assertion `left == right` failed");
+        View<IW, T> w = other.fresh();
+        const size_t ni = n_leaves<I0>;
+        if (groups_[ni].size() != 1 || w.groups()[ni].size() != 1) throw Unsupported("concat along an axis that is a merged group (to_usize) needs device div/mod");
+        const uint64_t nv = std::get<1>(sv), nw = std::get<1>(sw);
+        auto K = std::make_shared<Axis>(Axis{nv + nw});
+        Table tv{{groups_[ni][0].get(), rename_to(K)}}, tw;
+        for (size_t g = 0; g < groups_.size(); ++g) {
+            if (g == ni) continue;
+            if (groups_[g].size() != w.groups()[g].size()) throw Unsupported("concat of views whose axes are grouped differently");
+            for (size_t k = 0; k < groups_[g].size(); ++k) tw.push_back({w.groups()[g][k].get(), rename_to(groups_[g][k])});
+        }
+        Sub_ shifted; shifted.constant = -(int64_t)nv; shifted.terms.push_back({K, 1});
+        tw.push_back({w.groups()[ni][0].get(), shifted});
+        auto n = std::make_shared<Node>();
+        n->kind = MDIM_NODE_CONCAT; n->dtype = DType<T>::v; n->kids = {substitute(value_, tv), substitute(w.value(), tw)}; n->pairs.push_back({K, nullptr, nv});
+        Groups g = groups_; g[ni] = {K};
+        return View<Mid, T>(SizeOf<Mid>{std::get<0>(sv), nv + nw, std::get<2>(sv)}, g, NodeP(n));
+    }
+    // from_usize::<I, X, J>(size of X) (src/view.rs:352-363, 993-1021): the usize axis is re-indexed by X;
+    // its coordinate becomes x.to_usize(size), row-major over X's position axes.  (The reference takes a closure
+    // old_size -> X::Size; the caller evaluates it.)
+    template <class I0, class X, class J0> View<std::tuple<I0, X, J0>, T> from_usize(const SizeOf<X>& xsize) const {
+        using In = std::tuple<I0, usize, J0>;
+        using Out = std::tuple<I0, X, J0>;
+        auto s = to_iso_size<I, In>(size_);
+        if (length<X>(xsize) != std::get<1>(s))  // assert_eq!(X::length(size), old_size), src/view.rs:361
+            throw Panic(MDIM_ERR_SIZE, "assertion `left == right` failed\n  left: " + std::to_string(length<X>(xsize)) + "\n right: " + std::to_string(std::get<1>(s)));
+        const size_t ni = n_leaves<I0>;
+        if (groups_[ni].size() != 1) throw Unsupported("from_usize of an axis that is a merged group (to_usize) needs device div/mod");
+        Groups gx = fresh_groups<X>(xsize);
+        Sub_ sub; int64_t acc = 1; auto fx = flat(gx);
+        for (auto it = fx.rbegin(); it != fx.rend(); ++it) { sub.terms.push_back({*it, acc}); acc *= (int64_t)(*it)->length; }
+        Table t{{groups_[ni][0].get(), sub}};
+        Groups g(groups_.begin(), groups_.begin() + ni);
+        g.insert(g.end(), gx.begin(), gx.end());
+        g.insert(g.end(), groups_.begin() + ni + 1, groups_.end());
+        return View<Out, T>(SizeOf<Out>{std::get<0>(s), xsize, std::get<2>(s)}, g, substitute(value_, t));
+    }
+    // to_usize::<I, X, J>() (src/view.rs:373-378, 1029-1059): in position space an axis indexed by X and the usize
+    // axis of length X::length are the same run of positions; the merged axis is kept as ONE group of axes.
+    template <class I0, class X, class J0> View<std::tuple<I0, usize, J0>, T> to_usize() const {
+        using In = std::tuple<I0, X, J0>;
+        using Out = std::tuple<I0, usize, J0>;
+        auto s = to_iso_size<I, In>(size_);
+        const size_t ni = n_leaves<I0>, nx = n_leaves<X>;
+        Groups g(groups_.begin(), groups_.begin() + ni);
+        std::vector<AxisP> merged;
+        for (size_t k = ni; k < ni + nx; ++k) merged.insert(merged.end(), groups_[k].begin(), groups_[k].end());
+        g.push_back(merged);
+        g.insert(g.end(), groups_.begin() + ni + nx, groups_.end());
+        return View<Out, T>(SizeOf<Out>{std::get<0>(s), length<X>(std::get<1>(s)), std::get<2>(s)}, g, value_);
+    }
+    // insert_one::<I, J, K>(size) (src/view.rs:391-397): a new axis of type J and length 1
+    template <class I0, class J0, class K0> View<std::tuple<I0, J0, K0>, T> insert_one(const SizeOf<J0>& jsize) const {
+        using In = std::tuple<I0, K0>;
+        using Out = std::tuple<I0, J0, K0>;
+        if (length<J0>(jsize) != 1)  // src/view.rs:395
+            throw Panic(MDIM_ERR_SIZE, "assertion `left == right` failed\n  left: " + std::to_string(length<J0>(jsize)) + "\n right: 1");
+        auto s = to_iso_size<I, In>(size_);
+        Groups g(groups_.begin(), groups_.begin() + n_leaves<I0>);
+        Groups gj = fresh_groups<J0>(jsize);
+        g.insert(g.end(), gj.begin(), gj.end());
+        g.insert(g.end(), groups_.begin() + n_leaves<I0>, groups_.end());
+        return View<Out, T>(SizeOf<Out>{std::get<0>(s), jsize, std::get<1>(s)}, g, value_);
+    }
+    // remove_one::<I, J, K>() (src/view.rs:408-418): drop an axis of length 1 (its coordinate is pinned at 0)
+    template <class I0, class J0, class K0> View<std::tuple<I0, K0>, T> remove_one() const {
+        using In = std::tuple<I0, J0, K0>;
+        using Out = std::tuple<I0, K0>;
+        auto s = to_iso_size<I, In>(size_);
+        if (length<J0>(std::get<1>(s)) != 1)  // src/view.rs:413
+            throw Panic(MDIM_ERR_SIZE, "assertion `left == right` failed\n  left: " + std::to_string(length<J0>(std::get<1>(s))) + "\n right: 1");
+        const size_t ni = n_leaves<I0>, nj = n_leaves<J0>;
+        Table t;
+        for (size_t k = ni; k < ni + nj; ++k) for (auto& a : groups_[k]) t.push_back({a.get(), pin_at(0)});
+        Groups g(groups_.begin(), groups_.begin() + ni);
+        g.insert(g.end(), groups_.begin() + ni + nj, groups_.end());
+        return View<Out, T>(SizeOf<Out>{std::get<0>(s), std::get<2>(s)}, g, substitute(value_, t));
+    }
+    // map_axis::<I, V, J>(other) (src/view.rs:436-442, 1140-1170): at((i, x, j)) = self.at((i, other.at(x), j)) —
+    // a gather along ONE axis (`take`); `other` is a view of usize indices, bounds-checked like usize::to_usize.
+    template <class I0, class J0, class X> View<std::tuple<I0, X, J0>, T> map_axis(const View<X, usize>& other) const {
+        using In = std::tuple<I0, usize, J0>;
+        using Out = std::tuple<I0, X, J0>;
+        auto s = to_iso_size<I, In>(size_);
+        const size_t ni = n_leaves<I0>;
+        if (groups_[ni].size() != 1) throw Unsupported("map_axis along an axis that is a merged group (to_usize) needs device div/mod");
+        View<X, usize> w = other.fresh();
+        Groups g(groups_.begin(), groups_.begin() + ni);
+        g.insert(g.end(), w.groups().begin(), w.groups().end());
+        g.insert(g.end(), groups_.begin() + ni + 1, groups_.end());
+        return View<Out, T>(SizeOf<Out>{std::get<0>(s), w.size(), std::get<2>(s)}, g, gather(value_, groups_[ni][0], w.value()));
+    }
     // rows::<I, J>() (src/view.rs:617-622): on the device its one use is .fold<B>(init)
     template <class I0, class J0> Rows<View, I0, J0> rows() const { return Rows<View, I0, J0>(*this); }
 
   protected:
     static NodeP gather(const NodeP& n, const AxisP& ax, const NodeP& comp) {
         if (n->kind == MDIM_NODE_CONST) return n;
-        if (n->kind == MDIM_NODE_UNARY || n->kind == MDIM_NODE_BINARY) {
+        if (n->kind == MDIM_NODE_UNARY || n->kind == MDIM_NODE_BINARY || (n->kind == MDIM_NODE_CONCAT && n->pairs[0].a != ax)) {
             auto o = std::make_shared<Node>(*n); for (auto& k : o->kids) k = gather(k, ax, comp); return o;
         }
         if (n->kind == MDIM_NODE_LEAF || n->kind == MDIM_NODE_GATHER) {

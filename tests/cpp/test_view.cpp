@@ -86,6 +86,74 @@ int main(int argc, char** argv) {
         auto z = (col * rowv).collect(ex);
         CHECK(eq(z.as_ref(), {10.f, 20.f, 20.f, 40.f, 30.f, 60.f}));
     }
+    // ---- the index-manipulation algebra; strings are spelled as vocabulary positions -------
+    {   // src/view.rs:346-351: from_usize — (3,2,1) "A a B b C c" re-indexed as (usize, bool, usize)
+        using UBU = std::tuple<usize, bool, usize>;
+        Array<U3, usize> a(std::make_tuple(uint64_t(3), uint64_t(2), uint64_t(1)), {10, 11, 20, 21, 30, 31});
+        auto b = a.from_usize<usize, bool, usize>(Unit{}).collect(ex);
+        CHECK(b.at(UBU{2, true, 0}) == a.at(U3{2, 1, 0}));
+        CHECK(eq(b.as_ref(), a.as_ref()));
+        try { a.from_usize<usize, std::tuple<bool, bool>, usize>(std::make_tuple(Unit{}, Unit{})); CHECK(false); }
+        catch (const Panic& p) { CHECK(p.status == MDIM_ERR_SIZE); }  // assert_eq!(X::length(size), old_size), :361
+        // src/view.rs:367-372: to_usize — the inverse
+        Array<UBU, usize> c(std::make_tuple(uint64_t(3), Unit{}, uint64_t(1)), {10, 11, 20, 21, 30, 31});
+        auto d = c.to_usize<usize, bool, usize>().collect(ex);
+        CHECK(d.at(U3{2, 1, 0}) == c.at(UBU{2, true, 0}));
+        CHECK(d.size() == std::make_tuple(uint64_t(3), uint64_t(2), uint64_t(1)));
+        // a split axis keeps working under a transpose: (usize) -> (bool, Fixed<3>) -> swapped
+        Array<usize, usize> flat6(6, {0, 1, 2, 3, 4, 5});
+        auto sw = flat6.iso<std::tuple<Unit, usize, Unit>>().from_usize<Unit, std::tuple<bool, Fixed<3>>, Unit>(std::make_tuple(Unit{}, Unit{}))
+                      .iso<std::tuple<Unit, std::tuple<bool, Fixed<3>>, Unit>>().transpose<Unit, Fixed<3>, bool, Unit>();
+        CHECK(eq(sw.collect(ex).as_ref(), {0ull, 3ull, 1ull, 4ull, 2ull, 5ull}));
+    }
+    {   // src/view.rs:320-326: concat — [0,1,2] ++ [0,1] along the only axis
+        auto c = all(3).iso<std::tuple<Unit, usize, Unit>>().concat<Unit, Unit>(all(2).iso<std::tuple<Unit, usize, Unit>>()).collect(ex);
+        CHECK(eq(c.as_ref(), {0ull, 1ull, 2ull, 0ull, 1ull}));
+        Array<usize, usize> ap(2, {0, 1}), bo(2, {2, 3});  // the doctest itself: a.concat::<_, (), ()>(b).iso().collect()
+        CHECK(eq(ap.concat<Unit, Unit>(bo).iso<usize>().collect(ex).as_ref(), {0ull, 1ull, 2ull, 3ull}));
+        // along the outer and the inner axis of matrices; sizes off the axis must agree (:336-337)
+        Array<U2, float> a(std::make_tuple(uint64_t(2), uint64_t(3)), {1.f, 2.f, 3.f, 4.f, 5.f, 6.f});
+        Array<U2, float> b(std::make_tuple(uint64_t(1), uint64_t(3)), {7.f, 8.f, 9.f});
+        Array<U2, float> d(std::make_tuple(uint64_t(2), uint64_t(1)), {-1.f, -2.f});
+        using OUT = std::tuple<Unit, usize, usize>;
+        CHECK(eq(a.iso<OUT>().concat<Unit, usize>(b.iso<OUT>()).collect(ex).as_ref(), {1.f, 2.f, 3.f, 4.f, 5.f, 6.f, 7.f, 8.f, 9.f}));
+        using INN = std::tuple<usize, usize, Unit>;
+        CHECK(eq((a.iso<INN>().concat<usize, Unit>(d.iso<INN>()) * Scalar<float>(2.0f)).collect(ex).as_ref(), {2.f, 4.f, 6.f, -2.f, 8.f, 10.f, 12.f, -4.f}));
+        try { a.iso<OUT>().concat<Unit, usize>(d.iso<OUT>()); CHECK(false); } catch (const Panic& p) { CHECK(p.status == MDIM_ERR_SIZE); }
+        // a row of a concatenation picks one side at lowering time
+        CHECK(eq(a.iso<OUT>().concat<Unit, usize>(b.iso<OUT>()).iso<U2>().row<usize, usize>(2).collect(ex).as_ref(), {7.f, 8.f, 9.f}));
+    }
+    {   // src/view.rs:384-390, 401-407: insert_one / remove_one
+        using BB = std::tuple<bool, bool>;
+        using BUB = std::tuple<bool, usize, bool>;
+        Array<BB, usize> a(std::make_tuple(Unit{}, Unit{}), {0, 1, 2, 3});
+        auto b = a.insert_one<bool, usize, bool>(1).collect(ex);
+        CHECK(b.size() == std::make_tuple(Unit{}, uint64_t(1), Unit{}));
+        CHECK(eq(b.as_ref(), {0ull, 1ull, 2ull, 3ull}));
+        try { a.insert_one<bool, usize, bool>(2); CHECK(false); } catch (const Panic& p) { CHECK(p.status == MDIM_ERR_SIZE); }  // :395
+        Array<BUB, usize> c(std::make_tuple(Unit{}, uint64_t(1), Unit{}), {0, 1, 2, 3});
+        auto d = c.remove_one<bool, usize, bool>().collect(ex);
+        CHECK(d.size() == std::make_tuple(Unit{}, Unit{}));
+        CHECK(eq(d.as_ref(), {0ull, 1ull, 2ull, 3ull}));
+    }
+    {   // src/view.rs:423-435: map_axis — [2, 1] taken along the usize axis of a (bool, usize) Array
+        Array<usize, usize> a(2, {2, 1});
+        Array<std::tuple<bool, usize>, usize> b(std::make_tuple(Unit{}, uint64_t(3)), {0, 1, 2, 100, 101, 102});  // apple body crane / APPLE BODY CRANE
+        auto ab = b.map_axis<bool, Unit>(a).collect(ex);
+        CHECK(eq(ab.as_ref(), {2ull, 1ull, 102ull, 101ull}));
+        CHECK(ab.size() == std::make_tuple(Unit{}, uint64_t(2), Unit{}));
+        Array<usize, usize> bad(2, {2, 3});
+        try { b.map_axis<bool, Unit>(bad).collect(ex); CHECK(false); }
+        catch (const Panic& p) { CHECK(std::string(p.what()) == "Index 3 is out of bounds for size 3"); }  // src/int.rs:17
+        // rows of a float matrix taken by index (the bandwidth-friendly gather: contiguous inner axis)
+        std::vector<float> mv(5 * 8); for (size_t i = 0; i < mv.size(); ++i) mv[i] = 0.5f * (float)i;
+        Array<U2, float> m(std::make_tuple(uint64_t(5), uint64_t(8)), mv);
+        Array<usize, usize> pick(3, {4, 0, 4});
+        auto rows = m.map_axis<Unit, usize>(pick).collect(ex);
+        bool same = rows.as_ref().size() == 24;
+        for (size_t r = 0; r < 3 && same; ++r) for (size_t k = 0; k < 8; ++k) same = same && rows.as_ref()[r * 8 + k] == mv[(r == 1 ? 0 : 4) * 8 + k];
+        CHECK(same);
+    }
     // ---- the BASELINE configs in miniature --------------------------------------------------------------
     {   // config 2: a.zip(b).map(|(x,y)| x*y+1)  ==  a * b + Scalar(1.0)
         const uint64_t n = 1000;
