@@ -13,6 +13,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <map>
 #include <mutex>
@@ -146,6 +148,48 @@ std::string shape_key(const Program& P) {
 
 }  // namespace
 
+// ---- on-disk cache of compiled cubins -------------------------------------------------------------------------
+// A chain costs ~0.2 s of NVRTC the first time a PROCESS sees it; the cubin only depends on the generated source,
+// the embedded headers, the options and the compiler version, so when MDIM_JIT_CACHE names a directory it is
+// kept there as <fnv1a-64 of all of those>.cubin (opt-in: the library writes nowhere it was not told to).
+static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+    const unsigned char* p = (const unsigned char*)data;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+static std::string cache_dir() {
+    static const std::string dir = [] {
+        const char* e = getenv("MDIM_JIT_CACHE");
+        if (!e || !e[0] || (e[0] == '0' && !e[1])) return std::string();
+        const std::string d = e;
+        mkdir(d.c_str(), 0700);
+        struct stat st;
+        return stat(d.c_str(), &st) == 0 && S_ISDIR(st.st_mode) && access(d.c_str(), W_OK) == 0 ? d : std::string();
+    }();
+    return dir;
+}
+static bool cache_read(const std::string& path, std::vector<char>& cubin) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    bool ok = n > 64;
+    if (ok) { cubin.resize((size_t)n); ok = fread(cubin.data(), 1, (size_t)n, f) == (size_t)n && memcmp(cubin.data(), "\x7f" "ELF", 4) == 0; }
+    fclose(f);
+    if (!ok) cubin.clear();
+    return ok;
+}
+static void cache_write(const std::string& path, const std::vector<char>& cubin) {
+    char tmp[600];
+    snprintf(tmp, sizeof tmp, "%s.%d.tmp", path.c_str(), (int)getpid());
+    FILE* f = fopen(tmp, "wb");
+    if (!f) return;
+    const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    fclose(f);
+    if (!ok || rename(tmp, path.c_str()) != 0) unlink(tmp);  // rename is atomic: readers never see a partial file
+}
+
 // NVRTC: source -> sm_100a cubin.  Returns false (and the compiler log) on failure.
 static bool compile_cubin(const Plan& p, int maxr, int maxd, bool with_shape, std::vector<char>& cubin, std::string& log_out) {
     static Nvrtc nv;
@@ -156,7 +200,22 @@ static bool compile_cubin(const Plan& p, int maxr, int maxd, bool with_shape, st
     nvrtcProgram prog = nullptr;
     if (nv.create(&prog, src.c_str(), "mdim_jit.cu", 6, headers, names) != NVRTC_SUCCESS) { log_out = "nvrtcCreateProgram failed"; return false; }
     const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", "-lineinfo", "-DMDIM_NO_VEC256"};
-    const nvrtcResult rc = nv.compile(prog, nv.has_vec256 ? 4 : 5, opts);
+    const int n_opts = nv.has_vec256 ? 4 : 5;
+    std::string cached;
+    if (!cache_dir().empty() && !getenv("MDIM_JIT_DUMP")) {
+        uint64_t h = 14695981039346656037ull;
+        h = fnv1a(h, src.data(), src.size());
+        for (const char* hd : headers) h = fnv1a(h, hd, strlen(hd));
+        for (int i = 0; i < n_opts; ++i) h = fnv1a(h, opts[i], strlen(opts[i]) + 1);
+        int ver[2] = {0, 0};
+        if (nv.version) nv.version(&ver[0], &ver[1]);
+        h = fnv1a(h, ver, sizeof ver);
+        char name[64];
+        snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)h);
+        cached = cache_dir() + name;
+        if (cache_read(cached, cubin)) { nv.destroy(&prog); return true; }
+    }
+    const nvrtcResult rc = nv.compile(prog, n_opts, opts);
     if (rc != NVRTC_SUCCESS) {
         size_t n = 0; nv.log_size(prog, &n);
         std::vector<char> log(n + 1, 0); nv.log(prog, log.data());
@@ -168,6 +227,7 @@ static bool compile_cubin(const Plan& p, int maxr, int maxd, bool with_shape, st
     if (nv.cubin_size(prog, &n) == NVRTC_SUCCESS && n) { cubin.resize(n); if (nv.cubin(prog, cubin.data()) != NVRTC_SUCCESS) cubin.clear(); }
     nv.destroy(&prog);
     if (cubin.empty()) { log_out = "no cubin produced"; return false; }
+    if (!cached.empty()) cache_write(cached, cubin);
     if (const char* dir = getenv("MDIM_JIT_DUMP")) {  // for cuobjdump -sass
         static int counter = 0;
         char path[512];

@@ -2,6 +2,7 @@
 the ctypes mirror on struct layout, refuses to compute without a device, and plans the BASELINE chains
 onto the intended kernels (planning needs no GPU)."""
 import ctypes as C
+import os
 import re
 
 import numpy as np
@@ -92,3 +93,45 @@ def test_runtime_specialisation_compiles_without_a_gpu():
             pytest.skip("NVRTC is not installed")
         assert "specialised on first use" in v.describe()
         assert st == F.OK, log.value.decode()
+
+
+def test_jit_disk_cache(tmp_path):
+    """Compiled cubins are kept on disk (MDIM_JIT_CACHE): a second PROCESS does not pay NVRTC again."""
+    import subprocess
+    import sys
+    import time
+    script = r'''
+import ctypes as C, sys, time
+import numpy as np
+import multidimension_b200 as P
+from multidimension_b200 import usize, Array, Scalar, _ffi as F, lowering as L
+from multidimension_b200.view import _flat
+a = Array.new((usize, usize), (37, 24), np.arange(37 * 24, dtype=np.uint64))
+v = (a >> Scalar(3)).diagonal(7)
+groups, value = v._lower()
+em = L.emit(value, _flat(groups), "any")
+log = C.create_string_buffer(8000)
+t0 = time.perf_counter()
+st = F.lib().mdim_jit_check_nodevice(C.byref(em.expr), 0, log, 8000)
+print(st, time.perf_counter() - t0, log.value.decode()[:200])
+'''
+    env = dict(os.environ, MDIM_JIT_CACHE=str(tmp_path), PYTHONPATH=ROOT)
+    runs = []
+    for _ in range(2):
+        p = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=env, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        st, sec = p.stdout.split()[:2]
+        if int(st) == F.ERR_UNSUPPORTED and "NVRTC" in p.stdout:
+            pytest.skip("NVRTC is not installed")
+        assert int(st) == F.OK, p.stdout
+        runs.append(float(sec))
+    cubins = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
+    assert len(cubins) == 2, cubins          # the op-sequence kernel and its shape-specialised form
+    assert not [f for f in os.listdir(tmp_path) if f.endswith(".tmp")]
+    assert runs[1] < 0.5 * runs[0], runs     # the second process reads them back instead of compiling
+    del env["MDIM_JIT_CACHE"]                 # opt-in: without the variable nothing is written anywhere
+    home = tmp_path / "home"
+    home.mkdir()
+    env["HOME"] = env["XDG_CACHE_HOME"] = str(home)
+    p = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0 and not os.listdir(home)
