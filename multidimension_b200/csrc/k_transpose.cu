@@ -24,7 +24,10 @@
 
 namespace mdim {
 
-constexpr int tr_min_ctas(int smem_bytes) { return 227 * 1024 / (smem_bytes + 1024) > 8 ? 8 : 227 * 1024 / (smem_bytes + 1024); }
+// Resident CTAs per SM the register allocation aims for.  6 (40 registers) lets all four loads of a thread issue before
+// the first shared store; with 8 (32 registers) they go out two at a time.  Measured at 4096^2 on rotating buffers:
+// 8 -> 5 675 GB/s, 7 -> same code as 8, 6 -> 5 750, 5 -> 5 646.
+constexpr int tr_min_ctas(int smem_bytes) { return 227 * 1024 / (smem_bytes + 1024) > 6 ? 6 : 227 * 1024 / (smem_bytes + 1024); }
 
 // Address of element `e` of the source.  PEER: the Array is cut into equal blocks of peer_block elements, block p in
 // the HBM of GPU p (mapped into this process with CUDA IPC); the owner is e / peer_block, estimated in f32 and
@@ -42,7 +45,7 @@ __device__ __forceinline__ const char* tr_src(const TransposePlan& T, int64_t e)
 }
 
 template <int ES, bool VEC, int TAC, int TB, bool PEER>
-__global__ void __launch_bounds__(kTrThreads, PEER && tr_min_ctas(TB * TAC * 16) > 6 ? 6 : tr_min_ctas(TB * TAC * 16)) k_transpose(const __grid_constant__ TransposePlan T, void* __restrict__ out_v) {
+__global__ void __launch_bounds__(kTrThreads, tr_min_ctas(TB * TAC * 16)) k_transpose(const __grid_constant__ TransposePlan T, void* __restrict__ out_v) {
     constexpr int CH = 16 / ES;            // elements per 16-byte chunk
     constexpr int EW = ES / 4;             // 32-bit words per element
     constexpr int TA = TAC * CH;           // tile extent along A (elements); TAC chunks = TAC*16 bytes per source run
