@@ -271,3 +271,65 @@ def test_world2_gloo_sharded_flows(tmp_path):
         assert np.max(np.abs(p["red"] - want) / np.abs(want)) <= 1e-6
     idx = rng.integers(0, a.size, 4000).astype(np.uint64)
     assert_same_bits(np.concatenate([p["comp"] for p in parts]), a[idx.astype(np.int64)])
+
+
+# ---- world_size-2 gloo: peer-mapped flows.  The peers' blocks are POSIX shared memory here (CUDA IPC on the GPU
+#      box): every rank maps every block into its own address space and reads the owner's copy directly. ----------
+def _peer_worker(rank, world, port, out_dir):
+    import ctypes
+    from multiprocessing import shared_memory
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)  # the same global data on every rank; each publishes only its own block
+    M, Ncols, K = 12, 10, 4
+    full = rng.uniform(0, 1, M * Ncols * K).astype(np.float32)
+    block = equal_block(full.size, world)
+    mine = shared_memory.SharedMemory(create=True, size=block * 4)
+    local = np.ndarray(block, np.float32, buffer=mine.buf)
+    local[:] = 0
+    chunk = full[rank * block:(rank + 1) * block]
+    local[:chunk.size] = chunk
+    names = [None] * world
+    dist.all_gather_object(names, mine.name)  # the "IPC handle" exchange of sharding.peer_source
+    opened = [mine if r == rank else shared_memory.SharedMemory(name=names[r]) for r in range(world)]
+    views = [np.ndarray(block, np.float32, buffer=s.buf) for s in opened]
+    peers = PeerStorage(F.F32, full.size, [v.ctypes.data for v in views], block, keep=views)
+    dist.barrier()  # every block is filled before anyone reads a peer
+    # (1) transpose of the row-sharded (M, Ncols*K) matrix: this rank's block of the transposed rows
+    t_view = shard_view(Array((usize, usize), (M, Ncols * K), peers, "f32").transpose((), usize, usize, ()), rank, world)
+    tr = emu_collect(t_view)
+    # (2) fold over the sharded axis in index order, this rank's block of the (Ncols, K) result: bit-exact
+    whole = Array((usize, usize, usize), (M, Ncols, K), peers, "f32")
+    f_view = shard_view(fold_rows(whole.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize)), (usize, usize), usize, Add, np.float32(0)), rank, world)
+    fo = emu_collect(f_view)
+    # (3) gather with indices sharded, source peer-mapped
+    idx = rng.integers(0, full.size, 3000).astype(np.uint64)
+    ilo, ihi = shard_bounds(idx.size, world, rank)
+    ga = emu_collect(Array.new(usize, ihi - ilo, idx[ilo:ihi]).compose(Array(usize, full.size, peers, "f32")))
+    np.savez(os.path.join(out_dir, f"peer{rank}.npz"), tr=tr, fo=fo, ga=ga)
+    dist.barrier()  # nobody unmaps while a peer may still be reading
+    del peers, views, local
+    for r, s in enumerate(opened):
+        s.close()
+    dist.barrier()
+    mine.unlink()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_peer_mapped_flows(tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_peer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(os.path.join(tmp_path, f"peer{r}.npz")) for r in range(world)]
+    rng = np.random.default_rng(7)
+    M, Ncols, K = 12, 10, 4
+    full = rng.uniform(0, 1, M * Ncols * K).astype(np.float32)
+    assert_same_bits(np.concatenate([p["tr"] for p in parts]), full.reshape(M, Ncols * K).T.copy().reshape(-1))
+    seq = np.zeros(Ncols * K, np.float32)
+    for i in range(M):
+        seq = seq + full.reshape(M, Ncols * K)[i]
+    assert_same_bits(np.concatenate([p["fo"] for p in parts]), seq)  # bit-exact: no reassociation across ranks
+    idx = rng.integers(0, full.size, 3000).astype(np.uint64)
+    assert_same_bits(np.concatenate([p["ga"] for p in parts]), full[idx.astype(np.int64)])
