@@ -87,6 +87,14 @@ if "c1rot" in ops and args.reps:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (16 * args.reps)
     print(f"  c1rot: {ms:.4f} ms  {8 * m * m / ms / 1e6:.1f} GB/s", flush=True)
+if "c1peer" in ops:
+    # the peer-mapped transpose kernel on ONE GPU: 8 "peers" that are consecutive blocks of the same buffer (what the
+    # instruction overhead of the owner lookup costs when NVLink is not the limit)
+    from multidimension_b200.sharding import PeerStorage
+    m, world = 16384, 8
+    blk = m * m // world
+    peers = PeerStorage(F.F32, m * m, [big.data_ptr() + 4 * blk * p_ for p_ in range(world)], blk, keep=big, ctx=ctx)
+    run("c1peer", Array((usize, usize), (m, m), peers, "f32").transpose((), usize, usize, ()), out(tout[: m * m]), 8 * m * m)
 if "c1f64" in ops:
     m = 8192
     run("c1f64", dev((usize, usize), (m, m), big.view(torch.float64)[: m * m], "f64").transpose((), usize, usize, ()),
