@@ -82,7 +82,7 @@ typedef enum mdim_binary_op {
  *      and CONST (`Scalar`, src/view.rs:1399-1408) operands, exactly as `a*b + Scalar(1.0)`. ----- */
 typedef enum mdim_unary_op {
     MDIM_NEG = 0,  /* std::ops::Neg; wrapping for integers */
-    MDIM_NOT = 1,  /* std::ops::Not; bitwise on integers, logical on U8-as-bool */
+    MDIM_NOT = 1,  /* std::ops::Not on integers: bitwise (U8 included).  `!bool` is lowered by the host as x ^ 1 */
     MDIM_ABS = 2,
     MDIM_SQRT = 3, /* f32/f64 only, IEEE correctly rounded */
     MDIM_CAST = 4, /* Rust `as` between the dtypes above; source dtype in mdim_node.src_dtype */
@@ -183,6 +183,11 @@ int mdim_init(int device, mdim_ctx** ctx);
 int mdim_shutdown(mdim_ctx* ctx);
 /* Launch on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the context's own. */
 int mdim_set_stream(mdim_ctx* ctx, void* cuda_stream);
+/* The stream collects are launched on (a cudaStream_t): the context's own unless mdim_set_stream replaced it.  Record
+ * CUDA events on it to time collects.  On its OWN stream the context knows every kernel in flight, so a collect whose
+ * operands and output are untouched by the kernels still running starts before they finish (dependency-aware
+ * programmatic launch, csrc/launch.cuh); on a caller-owned stream every kernel waits for its predecessor. */
+int mdim_get_stream(mdim_ctx* ctx, void** cuda_stream);
 int mdim_sync(mdim_ctx* ctx); /* waits for the stream; returns the deferred status of async collects */
 int mdim_last_error(mdim_ctx* ctx, mdim_error_info* info);
 const char* mdim_status_string(int status);
@@ -199,7 +204,10 @@ int mdim_host_free(mdim_ctx* ctx, void* hptr);
 
 /* ---- the hot path ------------------------------------------------------------------------------ */
 /* View::collect (src/view.rs:146-150): materialise `e` into the dense row-major buffer `out`
- * (device memory, prod(length[0..rank)) elements of the root dtype, never aliasing an input). */
+ * (device memory, prod(length[0..rank)) elements of the root dtype, never aliasing an input).
+ * `out` must be aligned to its element size (else MDIM_ERR_INVALID); 16-byte alignment enables 128-bit stores and
+ * the TMA transpose, 32-byte alignment the 256-bit stores (cudaMalloc gives 256).  An output that is only
+ * element-aligned (a slice of a caller's tensor) is written with scalar stores. */
 int mdim_collect(mdim_ctx* ctx, const mdim_expr* e, void* out_device, uint32_t flags);
 
 /* Same, but every LEAF/GATHER `data` pointer and `out` are HOST buffers: uploads, collects and

@@ -69,6 +69,7 @@ SYMBOLS = [
     ("mdim_init", C.c_int, [C.c_int, _PP]),
     ("mdim_shutdown", C.c_int, [_P]),
     ("mdim_set_stream", C.c_int, [_P, _P]),
+    ("mdim_get_stream", C.c_int, [_P, _PP]),
     ("mdim_sync", C.c_int, [_P]),
     ("mdim_last_error", C.c_int, [_P, C.POINTER(ErrorInfo)]),
     ("mdim_status_string", C.c_char_p, [C.c_int]),

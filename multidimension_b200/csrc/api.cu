@@ -115,6 +115,11 @@ struct mdim_ctx {
     int eval_waves = 0;  // 0 = one trip per thread (non-persistent)
     int tr_ctas_cap = 0;                               // MDIM_TR_CTAS_PER_SM
     uint64_t pos_base = 0;  // applied to collects issued while a host collect is chunking
+    // Dependency-aware launches (launch.cuh): byte ranges touched by the kernels launched on own_stream since the last one
+    // that waited for its predecessor.  A launch that conflicts with none of them skips the wait.
+    struct Touched { uint64_t lo, hi; bool write; };
+    std::vector<Touched> inflight;
+    bool dep_tracking = true;  // MDIM_DEP_TRACK=0: every kernel waits (round-1 behaviour)
     size_t host_chunk_bytes = 128u << 20;  // measured: 8 MB 60.7, 32 MB 73.1, 128 MB 75.8, 512 MB 76.3 GB/s end to end
 };
 
@@ -155,7 +160,28 @@ bool plan_can_fail(const Plan& p) {
     return false;
 }
 
-int launch_eval(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err, bool explain, uint64_t explain_pos) {
+// May this launch start before its predecessor in the stream has finished?  Yes iff nothing it reads was written, and
+// nothing it writes was touched, by a kernel that may still be running.  Either way the launch is recorded.
+bool may_skip_wait(mdim_ctx* ctx, const Plan& p, const void* out) {
+    const bool usable = ctx->dep_tracking && pdl_enabled() && ctx->stream == ctx->own_stream && p.n_in_ranges >= 0;
+    mdim_ctx::Touched mine[kMaxRanges + 1];
+    int n = 0;
+    if (p.n_in_ranges >= 0)
+        for (int i = 0; i < p.n_in_ranges; ++i) mine[n++] = {p.in_range[i].lo, p.in_range[i].hi, false};
+    mine[n++] = {(uint64_t)(uintptr_t)out, (uint64_t)(uintptr_t)out + p.out_elems * (uint64_t)p.out_esize, true};
+    bool conflict = !usable || ctx->inflight.size() + (size_t)n > 256;
+    for (size_t k = 0; k < ctx->inflight.size() && !conflict; ++k) {
+        const mdim_ctx::Touched& t = ctx->inflight[k];
+        for (int i = 0; i < n; ++i)
+            if ((t.write || mine[i].write) && mine[i].lo < t.hi && t.lo < mine[i].hi) { conflict = true; break; }
+    }
+    if (conflict) ctx->inflight.clear();  // this kernel waits, so everything before it will have completed
+    if (usable) ctx->inflight.insert(ctx->inflight.end(), mine, mine + n);
+    else if (p.n_in_ranges < 0) ctx->inflight.push_back({0, ~0ull, true});  // untracked operands: conflicts with everything
+    return !conflict;
+}
+
+int launch_eval(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err, bool explain, uint64_t explain_pos, bool nowait = false) {
     const EvalVariant* v = select_variant(p, false);
     if (!v) return set_error(ctx, MDIM_ERR_UNSUPPORTED, "no evaluator instantiation for this expression");
     uint64_t g0 = 0, g1 = p.prog.n_vec;
@@ -166,6 +192,7 @@ int launch_eval(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err, bool expl
     Program q = p.prog;
     static const bool no256 = [] { const char* e = getenv("MDIM_NO_VEC256"); return e && e[0] == '1'; }();
     if (p.vec256_ok && !no256 && ((uintptr_t)out % 32) == 0) q.flags |= PF_VEC256;
+    if (nowait && !explain) q.flags |= PF_NOWAIT;
     if (explain) {
         q.flags |= PF_EXPLAIN;
         q.explain_pos = explain_pos;
@@ -193,25 +220,31 @@ int launch_eval(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err, bool expl
 }
 
 int launch_plan(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err) {
+    if (p.kind == KK_EMPTY) return MDIM_OK;
+    const bool nowait = may_skip_wait(ctx, p, out);
     switch (p.kind) {
-        case KK_EMPTY: return MDIM_OK;
         case KK_TRANSPOSE: {
             // Not persistent: far more CTAs than fit at once, so the hardware scheduler balances the tail.
             // Measured (B200, 16384^2 f32): 8/SM (resident set) 5.71 TB/s, 64/SM 6.18, 128/SM 6.32, one CTA per tile 6.35.
             const int per_sm = ctx->tr_ctas_cap > 0 ? ctx->tr_ctas_cap : 128;
             const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
             const int grid = (int)std::min<uint64_t>(p.tr.n_tiles, std::max<uint64_t>(cap, 1));
-            launch_transpose(p.tr, out, grid, ctx->stream);
+            TransposePlan tr = p.tr;
+            tr.nowait = nowait;
+            launch_transpose(tr, out, grid, ctx->stream);
             ctx->launches++;
             CU(ctx, cudaGetLastError());
             return MDIM_OK;
         }
-        case KK_FOLD_ROWS:
-            launch_fold_rows(p.fr, out, ctx->sm_count, ctx->stream);
+        case KK_FOLD_ROWS: {
+            FoldRowsPlan fr = p.fr;
+            fr.nowait = nowait;
+            launch_fold_rows(fr, out, ctx->sm_count, ctx->stream);
             ctx->launches++;
             CU(ctx, cudaGetLastError());
             return MDIM_OK;
-        default: return launch_eval(ctx, p, out, err, false, 0);
+        }
+        default: return launch_eval(ctx, p, out, err, false, 0, nowait);
     }
 }
 
@@ -252,6 +285,7 @@ int drain(mdim_ctx* ctx) {
     if (!ctx->pending.empty())
         CU(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(ErrWord) * kErrSlots, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->inflight.clear();  // nothing is running any more
     int result = MDIM_OK;
     std::vector<Pending> pend;
     pend.swap(ctx->pending);
@@ -303,6 +337,7 @@ int mdim_init(int device, mdim_ctx** out) {
     ctx->eval_ctas_per_sm = env_int("MDIM_EVAL_CTAS_PER_SM", 8);
     ctx->eval_waves = env_int("MDIM_EVAL_WAVES", 0);
     ctx->tr_ctas_cap = env_int("MDIM_TR_CTAS_PER_SM", 0);
+    ctx->dep_tracking = env_int("MDIM_DEP_TRACK", 1) != 0;
     ctx->host_chunk_bytes = (size_t)std::max(1, env_int("MDIM_HOST_CHUNK_MB", 128)) << 20;
     bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&ctx->d_err, sizeof(ErrWord) * kErrSlots) == cudaSuccess &&
@@ -352,6 +387,12 @@ int mdim_set_stream(mdim_ctx* ctx, void* cuda_stream) {
     int st = drain(ctx);
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return st;
+}
+
+int mdim_get_stream(mdim_ctx* ctx, void** cuda_stream) {
+    if (!ctx || !cuda_stream) return MDIM_ERR_INVALID;
+    *cuda_stream = (void*)ctx->stream;
+    return MDIM_OK;
 }
 
 int mdim_sync(mdim_ctx* ctx) {
@@ -458,6 +499,12 @@ int mdim_collect(mdim_ctx* ctx, const mdim_expr* e, void* out_device, uint32_t f
     int st = plan_expr(e, flags, plan, why, sizeof why);
     if (st) { delete plan; return set_error(ctx, st, why); }
     if (plan->kind != KK_EMPTY && !out_device) { delete plan; return set_error(ctx, MDIM_ERR_INVALID, "null output buffer"); }
+    if (plan->kind != KK_EMPTY && ((uintptr_t)out_device % (uintptr_t)plan->out_esize) != 0) { delete plan; return set_error(ctx, MDIM_ERR_INVALID, "output buffer is not aligned to its element size"); }
+    if (plan->kind != KK_EMPTY && ((uintptr_t)out_device % 16) != 0 && (plan->vec > 1 || plan->kind == KK_FOLD_ROWS)) {
+        // an element-aligned output (a slice of a caller's tensor): plan again with scalar stores
+        st = plan_expr(e, flags | kPlanScalarOut, plan, why, sizeof why);
+        if (st) { delete plan; return set_error(ctx, st, why); }
+    }
     cudaError_t ce = cudaSetDevice(ctx->device);
     if (ce != cudaSuccess) { delete plan; return cuda_fail(ctx, ce, "cudaSetDevice"); }
     st = collect_planned(ctx, plan, out_device, flags);

@@ -482,7 +482,7 @@ MDIM_FN uint32_t eval_preds(const Program& P, const ThreadState<WIDE, MAXR>& ts,
     using off_t = typename CoordTraits<WIDE>::off_t;
     uint32_t m = (1u << V) - 1u;
     for (int p = first; p < first + n; ++p) {
-        off_t s = 0;
+        off_t s = (off_t)ts.rk * (off_t)MDIM_SHAPE_OF(P).pred[p].rcoef;
 #pragma unroll
         for (int a = 0; a < MAXR; ++a) s += (off_t)ts.c[a] * (off_t)MDIM_SHAPE_OF(P).pred[p].coef[a];
         const off_t rhs = (off_t)MDIM_SHAPE_OF(P).pred[p].rhs, lc = (off_t)MDIM_SHAPE_OF(P).pred[p].lane_coef;

@@ -103,7 +103,7 @@ std::string make_shape_source(const Program& P) {
     }
     for (int i = 0; i < P.n_pred; ++i) {
         const Pred& Q = P.pred[i];
-        set("p.pred[%d].lane_coef=%d; p.pred[%d].cmp=%d; p.pred[%d].rhs=%lldll;", i, Q.lane_coef, i, Q.cmp, i, (long long)Q.rhs);
+        set("p.pred[%d].lane_coef=%d; p.pred[%d].cmp=%d; p.pred[%d].rcoef=%d; p.pred[%d].rhs=%lldll;", i, Q.lane_coef, i, Q.cmp, i, Q.rcoef, i, (long long)Q.rhs);
         for (int a = 0; a < kMaxRank; ++a) if (Q.coef[a]) set("p.pred[%d].coef[%d]=%d;", i, a, Q.coef[a]);
         s += "\n";
     }
@@ -123,11 +123,12 @@ std::string make_source(const Plan& p, int maxr, int maxd, bool with_shape) {
     }
     snprintf(buf, sizeof buf, "}; static constexpr int n = %d; }; }\n", p.prog.n_instr);
     s += buf;
-    char k[900];
+    char k[1200];
     snprintf(k, sizeof k,
              "extern \"C\" __global__ void __launch_bounds__(256) mdim_jit_kernel(const __grid_constant__ mdim::Program P, void* __restrict__ out, "
              "mdim::ErrWord* __restrict__ err, unsigned long long g_begin, unsigned long long g_end) {\n"
-             "  asm volatile(\"griddepcontrol.wait;\" ::: \"memory\"); asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");\n"
+             "  if (!(P.flags & mdim::PF_NOWAIT) || (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)) asm volatile(\"griddepcontrol.wait;\" ::: \"memory\");\n"
+             "  asm volatile(\"griddepcontrol.launch_dependents;\" ::: \"memory\");\n"
              "  const unsigned long long step = (unsigned long long)gridDim.x * 256ull;\n"
              "  for (unsigned long long g = g_begin + (unsigned long long)blockIdx.x * 256ull + threadIdx.x; g < g_end; g += step)\n"
              "    mdim::eval_vector<mdim::JitSig, %s, %d, %d, %s, %d, 1>(P, out, err, g);\n}\n",

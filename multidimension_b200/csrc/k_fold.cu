@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kFoldThreads)
 k_fold_rows(const __grid_constant__ FoldRowsPlan R, void* __restrict__ out_v, int n_warps, int stages, int ch, int skew, uint32_t q4_mul,
             uint32_t q4_shr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    pdl_entry();
+    pdl_entry(R.nowait != 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp >= n_warps) return;
     const uint32_t tile_words = (uint32_t)kRowsPerTile * (uint32_t)ch;
@@ -249,7 +249,7 @@ template <int L, bool FAST>
 __global__ void __launch_bounds__(256) k_fold_regs(const __grid_constant__ FoldRowsPlan R, void* __restrict__ out_v) {
     constexpr int M = 8;         // 16-byte chunks per lane
     constexpr int RPW = 32 / L;  // rows per warp
-    pdl_entry();
+    pdl_entry(R.nowait != 0);
     const int lane = threadIdx.x & 31, j = lane % L, grp = lane / L;
     const uint64_t warp = (uint64_t)blockIdx.x * (256 / 32) + (threadIdx.x >> 5);
     const uint64_t row = warp * RPW + grp;

@@ -19,7 +19,7 @@ constexpr int kEvalThreads = 256;
 template <class Sig, class S, int V, int MAXD, bool WIDE, int MAXR, int VPT>
 __global__ void __launch_bounds__(kEvalThreads)
 k_eval(const __grid_constant__ Program P, void* __restrict__ out, ErrWord* __restrict__ err, uint64_t g_begin, uint64_t g_end) {
-    pdl_entry();
+    pdl_entry((P.flags & PF_NOWAIT) != 0);
     const uint64_t step = (uint64_t)gridDim.x * kEvalThreads;
     for (uint64_t g = g_begin + (uint64_t)blockIdx.x * kEvalThreads + threadIdx.x; g < g_end; g += step)
         eval_vector<Sig, S, V, MAXD, WIDE, MAXR, VPT>(P, out, err, g);

@@ -6,6 +6,12 @@
 // overlap this grid's last wave instead of following it — worth ~10 % on a 20 us kernel such as the 4096^2
 // transpose, nothing on a millisecond one.  MDIM_PDL=0 turns the launch attribute off (the device side is
 // then a no-op).
+//
+// Round 2: dependency-aware launches.  The context (api.cu) tracks the memory ranges of the kernels launched since
+// the last one that really waited; a kernel whose operands and output touch none of them is launched with
+// `nowait`: its threads skip the wait, so its first wave overlaps the previous grid's last one (4096^2 transpose
+// back to back: 23.8 -> 20.5 us per launch).  ONE thread of such a grid still waits (the last CTA's thread 0), so
+// "grid N complete => every earlier grid complete" keeps holding and a later kernel that does wait is safe.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -35,8 +41,8 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 #if defined(__CUDACC__)
-__device__ __forceinline__ void pdl_entry() {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+__device__ __forceinline__ void pdl_entry(bool nowait = false) {
+    if (!nowait || (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)) asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 #endif

@@ -353,9 +353,11 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
                 memset(&pr, 0, sizeof pr);
                 const int a = axis_map[n.axis_a[p]];
                 const int b = n.axis_b[p] >= 0 ? axis_map[n.axis_b[p]] : -1;
-                pr.coef[pa(a)] += 1;
-                if (b >= 0) { pr.coef[pa(b)] -= 1; pr.rhs = (int64_t)n.axis_c[p]; }  // coord[a] == coord[b] + offset
-                else if (n.axis_c[p] >= len[a]) { pr.coef[pa(a)] = 0; pr.rhs = 1; }  // never on the diagonal
+                // the fastest reduction axis is counted by ThreadState::rk (its c[] entry stays 0): its coefficient is rcoef
+                auto term = [&](int g, int c) { if (red_rank > 0 && g == n_axes - 1) pr.rcoef += c; else pr.coef[pa(g)] += c; };
+                term(a, 1);
+                if (b >= 0) { term(b, -1); pr.rhs = (int64_t)n.axis_c[p]; }  // coord[a] == coord[b] + offset
+                else if (n.axis_c[p] >= len[a]) { memset(pr.coef, 0, sizeof pr.coef); pr.rcoef = 0; pr.rhs = 1; }  // never on the diagonal
                 else pr.rhs = (int64_t)n.axis_c[p];
                 pr.lane_coef = rank > 0 ? pr.coef[0] : 0;
                 P.pred[P.n_pred++] = pr; own_n++;
@@ -382,13 +384,16 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
             // Each side is evaluated under a lane mask (enclosing predicates + its own range test): its loads
             // would otherwise run past the end of the other operand.  src/view.rs:938-945.
             if (P.n_pred + 2 * (mask_n + 1) > kMaxPred) return why.fail(MDIM_ERR_UNSUPPORTED, "too many predicates");
-            const int axis = pa(axis_map[n.axis_a[0]]);
+            const int caxis = axis_map[n.axis_a[0]];
+            const bool on_rk = red_rank > 0 && caxis == n_axes - 1;  // concatenated along the fastest reduction axis
+            const int axis = pa(caxis);
             int first[2];
             for (int side = 0; side < 2; ++side) {
                 first[side] = P.n_pred;
                 for (int p = 0; p < mask_n; ++p) P.pred[P.n_pred++] = P.pred[mask_first + p];
                 Pred pr; memset(&pr, 0, sizeof pr);
-                pr.coef[axis] = 1; pr.rhs = (int64_t)std::min<uint64_t>(n.axis_c[0], len[axis_map[n.axis_a[0]]]); pr.cmp = side == 0 ? 1 : 2;
+                if (on_rk) pr.rcoef = 1; else pr.coef[axis] = 1;
+                pr.rhs = (int64_t)std::min<uint64_t>(n.axis_c[0], len[axis_map[n.axis_a[0]]]); pr.cmp = side == 0 ? 1 : 2;
                 pr.lane_coef = rank > 0 ? pr.coef[0] : 0;
                 P.pred[P.n_pred++] = pr;
             }
@@ -600,7 +605,7 @@ int Builder::detect_fast_paths() {
     }
     // (2) last-axis sequential fold of one contiguous f32/f64/int leaf, optionally fused with
     //     `x (eop) (fold [post_op c])` broadcast back over the folded axis (config C4)
-    if (fold_node >= 0 && red_rank == 1 && rank <= 2 && !plan->wide) {
+    if (fold_node >= 0 && red_rank == 1 && rank <= 2 && !plan->wide && !(flags & kPlanScalarOut)) {
         const mdim_node& F = N[fold_node];
         const int fc = child[fold_node][0];
         const uint64_t row_len = len[n_axes - 1];
@@ -657,6 +662,40 @@ int Builder::detect_fast_paths() {
 
 }  // namespace
 
+// Byte ranges the expression reads, from the descriptor alone: offset + sum over axes of stride * [0, length) (+ the
+// gathered components over [0, bound)).  Conservative by construction (a hull per operand).
+static void input_ranges(const mdim_expr* e, Plan* plan) {
+    plan->n_in_ranges = 0;
+    auto push = [&](uint64_t lo, uint64_t hi) {
+        if (plan->n_in_ranges < 0) return;
+        if (plan->n_in_ranges == kMaxRanges) { plan->n_in_ranges = -1; return; }
+        plan->in_range[plan->n_in_ranges++] = MemRange{lo, hi};
+    };
+    const int n_axes = e->rank + e->red_rank;
+    for (int i = 0; i < e->n_nodes; ++i) {
+        const mdim_node& n = e->nodes[i];
+        if (n.kind != MDIM_NODE_LEAF && n.kind != MDIM_NODE_GATHER) continue;
+        const uint64_t es = (uint64_t)dtype_size(n.dtype);
+        if (n.n_peers > 1) {
+            for (int p = 0; p < n.n_peers; ++p) push((uint64_t)(uintptr_t)n.peer[p], (uint64_t)(uintptr_t)n.peer[p] + n.peer_block * es);
+            continue;
+        }
+        int64_t lo = n.offset, hi = n.offset;
+        for (int a = 0; a < n_axes; ++a) {
+            if (e->length[a] == 0) continue;
+            const int64_t ext = n.stride[a] * (int64_t)(e->length[a] - 1);
+            if (ext > 0) hi += ext; else lo += ext;
+        }
+        if (n.kind == MDIM_NODE_GATHER)
+            for (int c = 0; c < n.n_comp; ++c) {
+                if (n.bound[c] == 0) continue;
+                const int64_t ext = n.gstride[c] * (int64_t)(n.bound[c] - 1);
+                if (ext > 0) hi += ext; else lo += ext;
+            }
+        push((uint64_t)((int64_t)(uintptr_t)n.data + lo * (int64_t)es), (uint64_t)((int64_t)(uintptr_t)n.data + (hi + 1) * (int64_t)es));
+    }
+}
+
 int plan_expr(const mdim_expr* e, uint32_t flags, Plan* plan, char* why_buf, size_t why_len) {
     Builder* b = new Builder();
     b->e = e; b->flags = flags; b->plan = plan; b->why = Why{why_buf, why_len};
@@ -674,6 +713,8 @@ int plan_expr(const mdim_expr* e, uint32_t flags, Plan* plan, char* why_buf, siz
         snprintf(plan->describe, sizeof plan->describe, "empty");
         delete b; return MDIM_OK;
     }
+    input_ranges(e, plan);
+    if (flags & kPlanScalarOut) b->force_vec = 1;
     b->canonical_axes();
     st = b->emit();
     if (st) { delete b; return st; }

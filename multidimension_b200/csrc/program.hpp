@@ -65,6 +65,7 @@ struct Pred {  // sum_a coef[a] * coord[a] (+ lane * lane_coef)  ==  rhs   (cmp 
                //                                              >=  rhs   (cmp 2: Concat, W side)
     int32_t coef[kMaxRank];
     int32_t lane_coef, cmp;  // lane_coef: coef of the innermost output axis
+    int32_t rcoef, pad;      // coef of the FASTEST reduction axis: its coordinate is ThreadState::rk, not c[] (like Addr::rstride)
     int64_t rhs;
 };
 
@@ -76,6 +77,7 @@ struct PeerTab {
 enum ProgFlags : uint32_t {
     PF_EXPLAIN = 1u,  // single-lane rerun that records mdim_error_info details
     PF_VEC256 = 2u,   // every vector operand and the output are 32-byte aligned: 256-bit loads / stores
+    PF_NOWAIT = 4u,   // no buffer of this launch is touched by a kernel still in flight: skip griddepcontrol.wait (launch.cuh)
 };
 
 struct Program {
@@ -144,6 +146,7 @@ struct TransposePlan {
     float peer_inv;              // 1 / peer_block (quotient estimate, corrected exactly in the kernel)
     uint64_t peer_block;
     const void* peer[MDIM_MAX_PEERS];
+    int32_t nowait;              // set per launch (api.cu): see launch.cuh
 };
 
 struct FoldRowsPlan {
@@ -161,7 +164,16 @@ struct FoldRowsPlan {
     int32_t has_post;
     uint64_t post_imm;    // ... with this constant on the right
     int32_t rows_per_cta;
+    int32_t nowait;       // set per launch (api.cu): see launch.cuh
 };
+
+// Memory a launch reads (api.cu adds the output and decides whether the kernel may skip griddepcontrol.wait).
+constexpr int kMaxRanges = 24;
+struct MemRange { uint64_t lo, hi; };  // [lo, hi) bytes
+
+// Internal planning flag (never part of the C ABI's MDIM_COLLECT_* set): the output buffer is only element-aligned
+// (e.g. a slice of someone else's tensor), so every store must be scalar and the vector-store fast paths are off.
+constexpr uint32_t kPlanScalarOut = 0x10000u;
 
 struct Plan {
     int32_t kind;
@@ -182,6 +194,8 @@ struct Plan {
     char sig[kMaxInstr * 4 + 4];  // signature bytes (opc,dtype,op,aux per instruction)
     int32_t sig_len;
     char describe[192];
+    MemRange in_range[kMaxRanges];  // every LEAF / GATHER source (and each peer block) as a byte range
+    int32_t n_in_ranges;            // -1: not tracked (too many operands): the launch waits for its predecessor
 };
 
 #ifndef __CUDACC_RTC__  // host-side declarations (this header is also compiled by NVRTC, see jit.cu)

@@ -223,6 +223,10 @@ def index_positions(I, index, size):
     if I is bool:
         return [1 if index else 0]
     if isinstance(I, Fixed):
+        # Fixed::to_usize is unchecked (src/int.rs:44) but the slice access items[to_usize] panics (src/array.rs:86)
+        if not (0 <= int(index) < I.n):
+            from ._ffi import Panic, ERR_OOB
+            raise Panic(ERR_OOB, f"Index {index} is out of bounds for size {I.n}")
         return [int(index)]
     if isinstance(I, Coated):
         return index_positions(I.inner, index, size)
@@ -236,3 +240,15 @@ def index_positions(I, index, size):
             k = k * n + p
         return [1 + k]
     raise IndexError_(f"not an index type: {I!r}")
+
+
+def index_leaves(I, index):
+    """The components of an index VALUE, one per NonTuple leaf of I (parallel to type_leaves)."""
+    if isinstance(I, tuple):
+        if not isinstance(index, tuple) or len(index) != len(I):
+            raise IndexError_(f"index {index!r} does not fit index type {I!r}")
+        out = []
+        for t, x in zip(I, index):
+            out.extend(index_leaves(t, x))
+        return out
+    return [index]

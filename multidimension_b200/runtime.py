@@ -46,6 +46,12 @@ class Context:
     def set_stream(self, cuda_stream):
         self.check(self.lib.mdim_set_stream(self.handle, C.c_void_p(cuda_stream or 0)))
 
+    def stream_handle(self):
+        """cudaStream_t the collects are launched on (wrap it with torch.cuda.ExternalStream to record events on it)."""
+        p = C.c_void_p()
+        self.check(self.lib.mdim_get_stream(self.handle, C.byref(p)))
+        return p.value or 0
+
     def sync(self):
         self.check(self.lib.mdim_sync(self.handle))
 

@@ -56,6 +56,8 @@ def shard_view(view, rank, world):
             first = next(i for i, (t, s) in enumerate(zip(types, leaves)) if X.leaf_lengths(t, s))
             if len(X.leaf_lengths(types[first], leaves[first])) != 1 or types[first] not in (X.usize, X.Reversed):
                 raise ValueError("the outermost axis must be a usize axis to be sharded")
+            if len(groups[first]) != 1:
+                raise L.Unsupported("the outermost axis has been re-split (to_usize / from_usize): shard before merging it")
             leaves = list(leaves)
             leaves[first] = self.hi - self.lo
             self.I, self.T = view.I, view.T

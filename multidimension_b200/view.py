@@ -78,10 +78,79 @@ def _split_groups(groups, *types):
     return out
 
 
-def _broadcast(I, J, si, sj, gi, gj, table):
+def _refine(lens_a, lens_b):
+    """Common refinement of two row-major factorisations of the same run of positions (e.g. an axis merged by
+    `to_usize` out of (2, 3) against a plain axis of 6, or (2, 6) against (4, 3)): -> (pieces, map_a, map_b) where
+    `pieces` are the lengths of the refined axes in row-major order and map_x[i] lists the pieces that make up axis i
+    of x, outermost first.  Raises Unsupported when no refinement exists (that remapping needs div/mod on the device)."""
+    if 0 in lens_a or 0 in lens_b:
+        raise Unsupported("re-splitting an empty axis")
+    pieces, map_a, map_b = [], [[] for _ in lens_a], [[] for _ in lens_b]
+    i = j = 0
+    ra = rb = None  # what is left of axis i of a / axis j of b (None: not loaded yet)
+    while True:
+        while ra is None and i < len(lens_a):
+            if lens_a[i] == 1:  # a unit axis is its own piece
+                map_a[i].append(len(pieces)); pieces.append(1); i += 1
+            else:
+                ra = lens_a[i]
+        while rb is None and j < len(lens_b):
+            if lens_b[j] == 1:
+                map_b[j].append(len(pieces)); pieces.append(1); j += 1
+            else:
+                rb = lens_b[j]
+        if ra is None or rb is None:
+            break
+        if ra % rb == 0:
+            step = rb
+        elif rb % ra == 0:
+            step = ra
+        else:
+            raise Unsupported(f"axis groups {lens_a} and {lens_b} have no common refinement: this remapping needs div/mod on the device")
+        map_a[i].append(len(pieces)); map_b[j].append(len(pieces)); pieces.append(step)
+        ra //= step
+        rb //= step
+        if ra == 1:
+            i += 1; ra = None
+        if rb == 1:
+            j += 1; rb = None
+    if ra is not None or rb is not None:
+        raise Unsupported(f"axis groups {lens_a} and {lens_b} do not describe the same run of positions")
+    return pieces, map_a, map_b
+
+
+def _sub_of(piece_axes):
+    """The coordinate of an axis cut into `piece_axes` (outermost first): row-major combination of the pieces."""
+    terms, acc = [], 1
+    for a in reversed(piece_axes):
+        if a.length != 1:  # the coordinate along a unit axis is always 0 (and the axis may not be iterated at all)
+            terms.append((a, acc))
+        acc *= a.length
+    return L.Sub(0, tuple(terms))
+
+
+def _unify_group(a, b, table_v, table_w):
+    """One leaf axis seen by both operands of a Zip / Concat as the groups `a` (self) and `b` (other): -> the group the
+    result iterates.  Identical splits are renamed 1:1; different splits of the same run of positions (an axis produced
+    by `to_usize`, src/view.rs:1029-1059) are both rewritten over their common refinement."""
+    la, lb = [x.length for x in a], [y.length for y in b]
+    if la == lb:
+        for x, y in zip(a, b):
+            table_w[y] = L.Sub(0, ((x, 1),))
+        return a
+    pieces, map_a, map_b = _refine(la, lb)
+    axes = [L.Axis(n) for n in pieces]
+    for x, idx in zip(a, map_a):
+        table_v[x] = _sub_of([axes[k] for k in idx])
+    for y, idx in zip(b, map_b):
+        table_w[y] = _sub_of([axes[k] for k in idx])
+    return axes
+
+
+def _broadcast(I, J, si, sj, gi, gj, table_v, table_w):
     """Broadcast::{Result,size} (src/broadcast.rs:22-162) + the axis unification that replaces
-    Broadcast::index: unified axes of `other` are renamed to `self`'s, missing ones stay absent
-    (stride 0).  gi/gj are consumed from the front."""
+    Broadcast::index: unified axes of `other` are rewritten in terms of `self`'s (table_w; table_v only when the two
+    sides split an axis differently), missing ones stay absent (stride 0).  gi/gj are consumed from the front."""
     if I == () and J == ():
         raise TypeError("() does not implement Broadcast<()> (Expand excludes (), src/broadcast.rs:4-9)")
     if I == ():
@@ -99,13 +168,11 @@ def _broadcast(I, J, si, sj, gi, gj, table):
         if si != sj:
             raise Panic(F.ERR_SIZE, "Unequal sizes")  # src/broadcast.rs:38
         a, b = gi.pop(0), gj.pop(0)
-        for x, y in zip(a, b):
-            table[y] = x
-        return I, si, [a]
+        return I, si, [_unify_group(a, b, table_v, table_w)]
     if ti and tj and len(I) == len(J):
         Rs, ss, gs = [], [], []
         for a, b, x, y in zip(I, J, si, sj):
-            R, s, g = _broadcast(a, b, x, y, gi, gj, table)
+            R, s, g = _broadcast(a, b, x, y, gi, gj, table_v, table_w)
             Rs.append(R); ss.append(s); gs.extend(g)
         return tuple(Rs), tuple(ss), gs
     raise TypeError(f"{I!r} does not implement Broadcast<{J!r}>")
@@ -145,7 +212,7 @@ class Sym:
     def __lshift__(self, o): return self._bin(o, O.Shl)
     def __rshift__(self, o): return self._bin(o, O.Shr)
     def __neg__(self): return Sym(_unary_node(O.Neg, self.node), self.T)
-    def __invert__(self): return Sym(_unary_node(O.Not, self.node), self.T)
+    def __invert__(self): return Sym(_unary_node(O.Not, self.node, self.T is bool), self.T)
     def __abs__(self): return Sym(_unary_node(O.Abs, self.node), self.T)
     def sqrt(self): return Sym(_unary_node(O.Sqrt, self.node), self.T)
 
@@ -164,9 +231,13 @@ def _binary_node(B, a, b):
     return L.Node(F.BINARY, a.dtype, op=B.code, children=(a, b))
 
 
-def _unary_node(U, a):
+def _unary_node(U, a, is_bool=False):
     if U.code == F.NOT and a.dtype in (F.F32, F.F64):
         raise TypeError("ops::Not is not implemented for floats")
+    if U.code == F.NOT and is_bool:  # `!bool` is logical: the descriptor's NOT is bitwise on U8, so lower it as x ^ true
+        return L.Node(F.BINARY, a.dtype, op=F.XOR, children=(a, L.Node(F.CONST, a.dtype, imm=1)))
+    if U.code in (F.NEG, F.ABS, F.SQRT) and is_bool:
+        raise TypeError(f"{U!r} is not implemented for bool")
     if U.code == F.SQRT and a.dtype not in (F.F32, F.F64):
         raise TypeError("sqrt is only defined for floats")
     return L.Node(F.UNARY, a.dtype, op=U.code, children=(a,), src_dtype=a.dtype)
@@ -512,10 +583,13 @@ def _iota_value(I, groups):
         g = next(it)
         if isinstance(t, (Coated, Option)):
             raise Unsupported(f"All<{t!r}> elements have no device representation")
-        (a,) = g
+        stride, acc = {}, 1
+        for a in reversed(g):  # a leaf whose group has been re-split: its value is the row-major position
+            stride[a] = acc
+            acc *= a.length
         if t is Reversed:  # src/int.rs:82-84: position p holds Reversed(size-1-p)
-            return L.Node(F.IOTA, F.U64, offset=a.length - 1, stride={a: -1})
-        n = L.Node(F.IOTA, F.U64, stride={a: 1})
+            return L.Node(F.IOTA, F.U64, offset=acc - 1, stride={a: -v for a, v in stride.items()})
+        n = L.Node(F.IOTA, F.U64, stride=stride)
         return _cast_node(n, F.U8) if t is bool else n
     return build(I)
 
@@ -599,7 +673,9 @@ class Map(View):
         groups, value = self.v._lower()
         f = self.f
         if isinstance(f, O.UnaryOp):
-            return groups, L.map_value(value, lambda n: _unary_node(f, n))
+            if isinstance(self.v.T, tuple):
+                raise TypeError(f"{f!r} is not implemented for tuple-typed elements")
+            return groups, _unary_node(f, value, self.v.T is bool)
         if isinstance(f, O.Cast):
             return groups, L.map_value(value, lambda n: _cast_node(n, dtype_of(f.T)))
         return groups, self._trace(value)[0]
@@ -705,7 +781,7 @@ class Zip(View):
         self.v, self.w, self.B = v, w, B
         # type and size now (panics with "Unequal sizes" like Zip::size), axes again at lowering time
         self.I, self._size, _ = _broadcast(v.I, w.I, v._size, w._size, [[] for _ in X.type_leaves(v.I)],
-                                           [[] for _ in X.type_leaves(w.I)], {})
+                                           [[] for _ in X.type_leaves(w.I)], {}, {})
         if B is O.Pair:
             self.T = (v.T, w.T)
         else:
@@ -716,9 +792,10 @@ class Zip(View):
     def _lower(self):
         gv, value_v = self.v._lower()
         gw, value_w = self.w._lower()
-        table = {}
-        _, _, groups = _broadcast(self.v.I, self.w.I, self.v._size, self.w._size, list(gv), list(gw), table)
-        value_w = L.map_value(value_w, _substituter(L.rename(table)))
+        table_v, table_w = {}, {}
+        _, _, groups = _broadcast(self.v.I, self.w.I, self.v._size, self.w._size, list(gv), list(gw), table_v, table_w)
+        value_v = L.map_value(value_v, _substituter(table_v))
+        value_w = L.map_value(value_w, _substituter(table_w))
         if self.B is O.Pair:
             return groups, (value_v, value_w)
         return groups, _binary_node(self.B, value_v, value_w)
@@ -768,9 +845,25 @@ class Transpose(View):  # src/view.rs:586-592, 1266-1294
 
 
 def _pin(groups, I, index, size):
-    """Substitution that fixes the axes of `groups` (indexed by I) at the positions of `index`."""
-    pos = X.index_positions(I, index, size)
-    return {a: L.Sub(p) for a, p in zip(_flat(groups), pos)}
+    """Substitution that fixes the axes of `groups` (indexed by I) at the positions of `index`.  A leaf whose group
+    has been re-split (to_usize / from_usize) is pinned through its LINEAR position, digit by digit."""
+    table = {}
+    for g, t, x, s in zip(groups, X.type_leaves(I), X.index_leaves(I, index), X.size_leaves(I, size)):
+        pos, lens = X.index_positions(t, x, s), X.leaf_lengths(t, s)
+        if [a.length for a in g] == lens:
+            digits = pos
+        else:
+            k = 0
+            for p_, n in zip(pos, lens):
+                k = k * n + p_
+            digits = []
+            for a in reversed(g):
+                digits.append(k % a.length if a.length else 0)
+                k = k // a.length if a.length else 0
+            digits.reverse()
+        for a, d in zip(g, digits):
+            table[a] = L.Sub(d)
+    return table
 
 
 class Row(View):  # src/view.rs:609-614, 1302-1322
@@ -864,14 +957,16 @@ class Concat(View):  # src/view.rs:327-339, 920-946
         if len(vk[0]) != 1 or len(wk[0]) != 1:
             raise Unsupported("concat along an axis that is a merged group (to_usize) needs device div/mod")
         K = L.Axis(self._size[1])
-        table_v = {vk[0][0]: L.Sub(0, ((K, 1),))}
-        table_w = {a: L.Sub(0, ((b, 1),)) for a, b in zip(_flat(wi) + _flat(wj), _flat(vi) + _flat(vj))}
+        table_v, table_w = {}, {}
+        gi = [_unify_group(a, b, table_v, table_w) for a, b in zip(vi, wi)]
+        gj = [_unify_group(a, b, table_v, table_w) for a, b in zip(vj, wj)]
+        table_v[vk[0][0]] = L.Sub(0, ((K, 1),))
         table_w[wk[0][0]] = L.Sub(-self._nv, ((K, 1),))  # W is addressed with k - len(V), :943
         sv, sw = _substituter(table_v), _substituter(table_w)
         lv, lw = L.flatten_value(value_v), L.flatten_value(value_w)
         out = [L.Node(F.CONCAT, a.dtype, children=(sv(a), sw(b)), pairs=((K, self._nv),)) for a, b in zip(lv, lw)]
         value = _build_like(self.T, list(out)) if isinstance(self.T, tuple) else out[0]
-        return vi + [[K]] + vj, value
+        return gi + [[K]] + gj, value
 
 
 class FromUsize(View):  # src/view.rs:352-363, 993-1021
@@ -889,13 +984,21 @@ class FromUsize(View):  # src/view.rs:352-363, 993-1021
         I, Xt, J = self._parts
         groups, value = self.v._lower()
         gi, gk, gj = _split_groups(groups, I, usize, J)
-        (k,) = gk[0]
-        gx = _fresh_groups(Xt, self._xsize)
-        terms, acc = [], 1
-        for a in reversed(_flat(gx)):  # x.to_usize(size): row-major over X's axes (:1019)
-            terms.append((a, acc))
-            acc *= a.length
-        value = L.map_value(value, _substituter({k: L.Sub(0, tuple(terms))}))
+        # x.to_usize(size) is row-major over X's position axes (:1019); the usize axis may itself be a merged group
+        # (a to_usize further down), so both factorisations are rewritten over their common refinement
+        old = gk[0]
+        lens_x = [n for t, sz in zip(X.type_leaves(Xt), X.size_leaves(Xt, self._xsize)) for n in X.leaf_lengths(t, sz)]
+        pieces, map_old, map_x = _refine([a.length for a in old], lens_x)
+        axes = [L.Axis(n) for n in pieces]
+        table = {a: _sub_of([axes[k] for k in idx]) for a, idx in zip(old, map_old)}
+        gx, at = [], 0
+        for t, sz in zip(X.type_leaves(Xt), X.size_leaves(Xt, self._xsize)):
+            g = []
+            for _ in X.leaf_lengths(t, sz):
+                g.extend(axes[k] for k in map_x[at])
+                at += 1
+            gx.append(g)
+        value = L.map_value(value, _substituter(table))
         return gi + gx + gj, value
 
 

@@ -21,9 +21,13 @@ ops = args.ops.split(",")
 torch.cuda.set_device(0)
 ctx = P.Context(0)
 P.set_default_context(ctx)
-stream = torch.cuda.Stream()
-torch.cuda.set_stream(stream)
-ctx.set_stream(stream.cuda_stream)
+if os.environ.get("MDIM_OPS_TORCH_STREAM") == "1":  # a caller-owned stream: every kernel waits for its predecessor
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    torch.cuda.set_stream(stream)
+else:  # the context's own stream (dependency-aware launches), wrapped only so that torch events can be recorded on it;
+    # torch's own kernels stay on torch's stream, separated from the collects by device-wide synchronisation
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=0)
 
 
 def dev(I, size, t, T):
@@ -36,6 +40,7 @@ def out(t, dt=F.F32):
 
 def run(name, view, o, alg_bytes):
     print(name, view.describe(args.flags), flush=True)
+    torch.cuda.synchronize()
     view.collect(out=o, flags=args.flags)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -75,6 +80,7 @@ if "c1rot" in ops and args.reps:
     m = 4096
     preps = [dev((usize, usize), (m, m), big[k * m * m: (k + 1) * m * m], "f32").transpose((), usize, usize, ())
              .prepare(out=out(tout[k * m * m: (k + 1) * m * m]), flags=args.flags | F.COLLECT_ASYNC) for k in range(16)]
+    torch.cuda.synchronize()
     for p_ in preps:
         p_.run()
     ctx.sync()
