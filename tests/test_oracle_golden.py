@@ -226,3 +226,14 @@ def test_product_library_is_fresh():
     src = glob.glob(os.path.join(os.path.dirname(LIB_PATH), "csrc", "*.*")) + [os.path.join(os.path.dirname(LIB_PATH), "..", "include", "mdim.h")]
     newest = max(os.path.getmtime(p) for p in src if not p.endswith(".log"))
     assert os.path.getmtime(LIB_PATH) >= newest, "libmdim_b200.so is older than its sources: run __graft_entry__.build()"
+
+
+def test_golden_vectors_are_extracted_from_the_reference_sources():
+    """tests/golden/doctests.json must be exactly what make_doctest_vectors.py parses out of the assert_eq! lines of
+    /root/reference/src/*.rs (build container only: the reference does not travel to the GPU box)."""
+    import os, subprocess, sys
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("the reference sources are not present on this machine")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_doctest_vectors.py")
+    r = subprocess.run([sys.executable, script, "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
