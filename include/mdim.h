@@ -47,7 +47,8 @@ typedef enum mdim_status {
     MDIM_ERR_CUDA = 4,        /* CUDA runtime/driver failure, or no sm_100 device                    */
     MDIM_ERR_ARITH = 5,       /* integer division/remainder by zero, or MIN / -1 (Rust panics)       */
     MDIM_ERR_INVALID = 6,     /* malformed descriptor (bad arity, dtype mismatch, null pointer ...)   */
-    MDIM_ERR_NOMEM = 7
+    MDIM_ERR_NOMEM = 7,
+    MDIM_ERR_NCCL = 8         /* NCCL missing or a collective failed (multi-GPU entry points only)             */
 } mdim_status;
 
 /* ---- element types. `usize` of the reference is MDIM_U64 ------------------------------------- */
@@ -76,6 +77,9 @@ typedef enum mdim_binary_op {
     MDIM_SHR = 9, /* ops::Shr    src/ops.rs:123 */
     MDIM_BINARY_COUNT = 10
 } mdim_binary_op;
+/* extra reduction operators accepted by mdim_allreduce only (a fold with a closure `|s, x| s.min(x)`) */
+#define MDIM_REDUCE_MIN 100
+#define MDIM_REDUCE_MAX 101
 
 /* ---- closed unary vocabulary standing in for `Map`'s opaque closure (src/view.rs:880-889);
  *      same type-level style as ops.rs.  Affine maps such as x*y+1 are spelled with BINARY nodes
@@ -226,6 +230,28 @@ int mdim_plan_describe_nodevice(const mdim_expr* e, uint32_t flags, char* buf, s
 int mdim_ipc_export(mdim_ctx* ctx, void* dptr, uint8_t handle[MDIM_IPC_HANDLE_BYTES]);
 int mdim_ipc_open(mdim_ctx* ctx, const uint8_t handle[MDIM_IPC_HANDLE_BYTES], void** dptr);
 int mdim_ipc_close(mdim_ctx* ctx, void* dptr);
+
+/* ---- multi-GPU: one process per GPU, one context per process -----------------------------------------
+ * The reference has no distributed layer; this is the surface a sharded `DeviceArray` needs so that the Rust host (or
+ * the C++ / Python mirrors) can partition Arrays along the outermost index WITHOUT any other runtime:
+ *   - a communicator (NCCL, loaded at run time; rank 0 makes the id, the caller ships its 128 bytes to the other
+ *     ranks by any means it has — a file, a socket, MPI, an environment variable);
+ *   - the two collectives the north star names, on the context's stream: all-gather of a sharded compose() source
+ *     (src/view.rs:897-912) and all-reduce of the partial folds over a sharded axis (src/view.rs:617-622);
+ *   - the peer table: every rank's block mapped into every process (CUDA IPC), for mdim_node.peer[] — the gather,
+ *     transpose and fold kernels then read the owning GPU's HBM over NVLink inside the kernel, no collective.
+ * All of these are COLLECTIVE calls: every rank of the communicator makes them in the same order. */
+#define MDIM_COMM_ID_BYTES 128
+int mdim_comm_unique_id(uint8_t id[MDIM_COMM_ID_BYTES]);                                 /* rank 0 */
+int mdim_comm_init(mdim_ctx* ctx, int rank, int world, const uint8_t id[MDIM_COMM_ID_BYTES]);
+int mdim_comm_destroy(mdim_ctx* ctx);
+int mdim_comm_info(mdim_ctx* ctx, int* rank, int* world, int* nccl_version);
+int mdim_allgather(mdim_ctx* ctx, const void* send_device, void* recv_device, size_t block_bytes); /* async, rank-major */
+int mdim_allreduce(mdim_ctx* ctx, void* data_device, size_t n, int dtype, int op);       /* async, in place; op: MDIM_ADD,
+                                                                                             MDIM_MUL, MDIM_REDUCE_MIN/MAX */
+int mdim_barrier(mdim_ctx* ctx);                                                          /* + waits for the stream */
+int mdim_peer_table(mdim_ctx* ctx, void* local_device, size_t block_bytes, void* peers[MDIM_MAX_PEERS]);
+int mdim_peer_table_close(mdim_ctx* ctx);                                                 /* unmaps every peer block */
 
 /* Run-time specialisation (NVRTC) of `e`'s op tree, compile step only: needs no GPU.  0 = compiles for
  * sm_100a; MDIM_ERR_UNSUPPORTED = NVRTC not installed or the plan has a pre-built kernel; `log` gets details. */

@@ -15,7 +15,9 @@ MAX_PEERS = 8
 ABI_VERSION = 1
 
 # status codes (mdim_status)
-OK, ERR_OOB, ERR_SIZE, ERR_UNSUPPORTED, ERR_CUDA, ERR_ARITH, ERR_INVALID, ERR_NOMEM = range(8)
+OK, ERR_OOB, ERR_SIZE, ERR_UNSUPPORTED, ERR_CUDA, ERR_ARITH, ERR_INVALID, ERR_NOMEM, ERR_NCCL = range(9)
+COMM_ID_BYTES = 128
+REDUCE_MIN, REDUCE_MAX = 100, 101
 
 # dtypes (mdim_dtype)
 U8, I32, U32, I64, U64, F32, F64 = range(7)
@@ -88,6 +90,15 @@ SYMBOLS = [
     ("mdim_ipc_export", C.c_int, [_P, _P, C.POINTER(C.c_uint8)]),
     ("mdim_ipc_open", C.c_int, [_P, C.POINTER(C.c_uint8), _PP]),
     ("mdim_ipc_close", C.c_int, [_P, _P]),
+    ("mdim_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)]),
+    ("mdim_comm_init", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_uint8)]),
+    ("mdim_comm_destroy", C.c_int, [_P]),
+    ("mdim_comm_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("mdim_allgather", C.c_int, [_P, _P, _P, C.c_size_t]),
+    ("mdim_allreduce", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int]),
+    ("mdim_barrier", C.c_int, [_P]),
+    ("mdim_peer_table", C.c_int, [_P, _P, C.c_size_t, _PP]),
+    ("mdim_peer_table_close", C.c_int, [_P]),
     ("mdim_jit_check_nodevice", C.c_int, [C.POINTER(Expr), C.c_uint32, C.c_char_p, C.c_size_t]),
     ("mdim_abi_version", C.c_int, []),
 ]

@@ -1,0 +1,281 @@
+// comm.cu — the multi-GPU surface of the C ABI (include/mdim.h, "one process per GPU"): an NCCL communicator
+// bound to the context, the two collectives the north star names (all-gather of a sharded compose() source,
+// all-reduce of the partial folds over a sharded axis), and the peer table that lets the gather / transpose /
+// fold kernels read the other GPUs' blocks directly over NVLink (CUDA IPC handles exchanged over the communicator).
+//
+// NCCL is loaded at run time (dlopen of libnccl.so.2: the copy already in the process if the host program has one,
+// e.g. the NCCL bundled with torch, else the system library): the library has no link-time dependency on it, and a
+// single-GPU user never needs it.  Only a handful of long-stable entry points are used, declared below with NCCL's
+// own ABI (ncclUniqueId is 128 bytes; ncclDataType_t / ncclRedOp_t values are fixed by nccl.h since 2.0).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "ctx.hpp"
+
+namespace mdim {
+
+namespace {
+
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+enum { kNcclSuccess = 0 };
+// ncclDataType_t
+enum { kNcclInt8 = 0, kNcclUint8 = 1, kNcclInt32 = 2, kNcclUint32 = 3, kNcclInt64 = 4, kNcclUint64 = 5, kNcclFloat32 = 7, kNcclFloat64 = 8 };
+// ncclRedOp_t
+enum { kNcclSum = 0, kNcclProd = 1, kNcclMax = 2, kNcclMin = 3 };
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GetVersion)(int*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    char why[160] = {0};
+};
+
+NcclApi& nccl() {
+    static NcclApi api = [] {
+        NcclApi a;
+        const char* names[] = {getenv("MDIM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n || !*n) continue;
+            a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (a.lib) break;
+        }
+        if (!a.lib) { snprintf(a.why, sizeof a.why, "libnccl.so.2 not found (%s)", dlerror()); return a; }
+#define SYM(field, name) *(void**)(&a.field) = dlsym(a.lib, name); if (!a.field) { snprintf(a.why, sizeof a.why, "libnccl lacks %s", name); return a; }
+        SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy") SYM(AllGather, "ncclAllGather")
+        SYM(AllReduce, "ncclAllReduce") SYM(GetVersion, "ncclGetVersion") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+        a.ok = true;
+        return a;
+    }();
+    return api;
+}
+
+int nccl_fail(mdim_ctx* ctx, int rc, const char* what) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "%s: %s", what, nccl().GetErrorString ? nccl().GetErrorString(rc) : "NCCL error");
+    return ctx ? set_error(ctx, MDIM_ERR_NCCL, msg) : MDIM_ERR_NCCL;
+}
+
+#define NC(ctx, call)                                         \
+    do {                                                      \
+        int rc_ = (call);                                     \
+        if (rc_ != kNcclSuccess) return nccl_fail(ctx, rc_, #call); \
+    } while (0)
+
+}  // namespace
+
+struct Comm {
+    NcclComm comm = nullptr;
+    int rank = 0, world = 1;
+    char* scratch = nullptr;  // device staging for the small host-side exchanges (IPC handles, barrier word)
+    size_t scratch_bytes = 0;
+    struct Opened { cudaIpcMemHandle_t handle; void* base; };  // one mapping per peer ALLOCATION, however many blocks live in it
+    std::vector<Opened> opened;  // IPC mappings made by mdim_peer_table, closed by mdim_peer_table_close / shutdown
+};
+
+void comm_destroy(mdim_ctx* ctx) {
+    Comm* c = ctx->comm;
+    if (!c) return;
+    for (const Comm::Opened& o : c->opened) cudaIpcCloseMemHandle(o.base);
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    delete c;
+    ctx->comm = nullptr;
+}
+
+namespace {
+
+// all-gather `bytes` of host data per rank through the communicator: -> out[world * bytes]
+int exchange_host(mdim_ctx* ctx, const void* mine, size_t bytes, void* out) {
+    Comm* c = ctx->comm;
+    const size_t need = bytes * (size_t)(c->world + 1);
+    if (need > c->scratch_bytes) {
+        if (c->scratch) CU(ctx, cudaFree(c->scratch));
+        c->scratch = nullptr;
+        CU(ctx, cudaMalloc(&c->scratch, need));
+        c->scratch_bytes = need;
+    }
+    char* send = c->scratch + bytes * (size_t)c->world;
+    CU(ctx, cudaMemcpyAsync(send, mine, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NC(ctx, nccl().AllGather(send, c->scratch, bytes, kNcclUint8, c->comm, ctx->stream));
+    poison_inflight(ctx);
+    CU(ctx, cudaMemcpyAsync(out, c->scratch, bytes * (size_t)c->world, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return MDIM_OK;
+}
+
+typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+GetAddressRangeFn address_range_fn() {
+    static const GetAddressRangeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (GetAddressRangeFn)p;
+    }();
+    return fn;
+}
+
+struct PeerRecord {  // what every rank publishes about its block
+    cudaIpcMemHandle_t handle;  // of the ALLOCATION the block lives in (cudaIpcGetMemHandle ignores interior offsets)
+    uint64_t offset;            // of the block inside that allocation
+    uint64_t bytes;
+};
+
+}  // namespace
+}  // namespace mdim
+
+using namespace mdim;
+
+extern "C" {
+
+int mdim_comm_unique_id(uint8_t id[MDIM_COMM_ID_BYTES]) {
+    if (!id) return MDIM_ERR_INVALID;
+    static_assert(sizeof(NcclId) == MDIM_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    if (!nccl().ok) return MDIM_ERR_NCCL;
+    NcclId u;
+    if (nccl().GetUniqueId(&u) != kNcclSuccess) return MDIM_ERR_NCCL;
+    memcpy(id, &u, sizeof u);
+    return MDIM_OK;
+}
+
+int mdim_comm_init(mdim_ctx* ctx, int rank, int world, const uint8_t id[MDIM_COMM_ID_BYTES]) {
+    if (!ctx || !id || world < 1 || rank < 0 || rank >= world || world > MDIM_MAX_PEERS) return MDIM_ERR_INVALID;
+    if (ctx->comm) return set_error(ctx, MDIM_ERR_INVALID, "the context already has a communicator");
+    if (!nccl().ok) return set_error(ctx, MDIM_ERR_NCCL, nccl().why);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Comm* c = new (std::nothrow) Comm();
+    if (!c) return MDIM_ERR_NOMEM;
+    c->rank = rank; c->world = world;
+    NcclId u;
+    memcpy(&u, id, sizeof u);
+    const int rc = nccl().CommInitRank(&c->comm, world, u, rank);
+    if (rc != kNcclSuccess) { delete c; return nccl_fail(ctx, rc, "ncclCommInitRank"); }
+    ctx->comm = c;
+    return MDIM_OK;
+}
+
+int mdim_comm_destroy(mdim_ctx* ctx) {
+    if (!ctx) return MDIM_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    comm_destroy(ctx);
+    return MDIM_OK;
+}
+
+int mdim_comm_info(mdim_ctx* ctx, int* rank, int* world, int* nccl_version) {
+    if (!ctx) return MDIM_ERR_INVALID;
+    if (rank) *rank = ctx->comm ? ctx->comm->rank : 0;
+    if (world) *world = ctx->comm ? ctx->comm->world : 1;
+    if (nccl_version) { *nccl_version = 0; if (nccl().ok) nccl().GetVersion(nccl_version); }
+    return MDIM_OK;
+}
+
+// ncclAllGather of every rank's `block_bytes` into `recv` (rank-major), on the context's stream, asynchronous.
+int mdim_allgather(mdim_ctx* ctx, const void* send_device, void* recv_device, size_t block_bytes) {
+    if (!ctx || !ctx->comm) return ctx ? set_error(ctx, MDIM_ERR_INVALID, "no communicator: call mdim_comm_init") : MDIM_ERR_INVALID;
+    if (!block_bytes) return MDIM_OK;
+    if (!send_device || !recv_device) return MDIM_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    NC(ctx, nccl().AllGather(send_device, recv_device, block_bytes, kNcclUint8, ctx->comm->comm, ctx->stream));
+    poison_inflight(ctx);
+    return MDIM_OK;
+}
+
+// ncclAllReduce in place over `n` elements of `dtype` with the fold's operator (ADD, MUL, or the min / max of the
+// MDIM_REDUCE_* codes), on the context's stream, asynchronous.  f32 sums are reassociated: 1e-6 relative tolerance.
+int mdim_allreduce(mdim_ctx* ctx, void* data_device, size_t n, int dtype, int op) {
+    if (!ctx || !ctx->comm) return ctx ? set_error(ctx, MDIM_ERR_INVALID, "no communicator: call mdim_comm_init") : MDIM_ERR_INVALID;
+    if (!n) return MDIM_OK;
+    if (!data_device) return MDIM_ERR_INVALID;
+    int nt, no;
+    switch (dtype) {
+        case MDIM_U8: nt = kNcclUint8; break;
+        case MDIM_I32: nt = kNcclInt32; break;
+        case MDIM_U32: nt = kNcclUint32; break;
+        case MDIM_I64: nt = kNcclInt64; break;
+        case MDIM_U64: nt = kNcclUint64; break;
+        case MDIM_F32: nt = kNcclFloat32; break;
+        case MDIM_F64: nt = kNcclFloat64; break;
+        default: return set_error(ctx, MDIM_ERR_INVALID, "bad dtype");
+    }
+    switch (op) {
+        case MDIM_ADD: no = kNcclSum; break;
+        case MDIM_MUL: no = kNcclProd; break;
+        case MDIM_REDUCE_MIN: no = kNcclMin; break;
+        case MDIM_REDUCE_MAX: no = kNcclMax; break;
+        default: return set_error(ctx, MDIM_ERR_UNSUPPORTED, "all-reduce supports ADD, MUL, MIN and MAX");
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    NC(ctx, nccl().AllReduce(data_device, data_device, n, nt, no, ctx->comm->comm, ctx->stream));
+    poison_inflight(ctx);
+    return MDIM_OK;
+}
+
+// Every rank has finished everything it enqueued before its own call (a 4-byte all-reduce + stream sync).
+int mdim_barrier(mdim_ctx* ctx) {
+    if (!ctx || !ctx->comm) return ctx ? set_error(ctx, MDIM_ERR_INVALID, "no communicator: call mdim_comm_init") : MDIM_ERR_INVALID;
+    uint32_t one = 1, all[MDIM_MAX_PEERS];
+    CU(ctx, cudaSetDevice(ctx->device));
+    return exchange_host(ctx, &one, sizeof one, all);
+}
+
+// Collective.  Every rank passes its own block (device memory, any interior pointer of a cudaMalloc allocation);
+// on return peers[p] addresses rank p's block from THIS process (peers[rank] == local_device), mapped with CUDA IPC
+// and readable by the kernels over NVLink / NVSwitch (mdim_node.peer[]).
+int mdim_peer_table(mdim_ctx* ctx, void* local_device, size_t block_bytes, void* peers[MDIM_MAX_PEERS]) {
+    if (!ctx || !ctx->comm) return ctx ? set_error(ctx, MDIM_ERR_INVALID, "no communicator: call mdim_comm_init") : MDIM_ERR_INVALID;
+    if (!local_device || !peers) return MDIM_ERR_INVALID;
+    Comm* c = ctx->comm;
+    CU(ctx, cudaSetDevice(ctx->device));
+    PeerRecord mine;
+    memset(&mine, 0, sizeof mine);
+    CUdeviceptr base = (CUdeviceptr)(uintptr_t)local_device;
+    size_t alloc_size = 0;
+    if (GetAddressRangeFn fn = address_range_fn()) {
+        if (fn(&base, &alloc_size, (CUdeviceptr)(uintptr_t)local_device) != CUDA_SUCCESS) base = (CUdeviceptr)(uintptr_t)local_device;
+    }
+    CU(ctx, cudaIpcGetMemHandle(&mine.handle, (void*)(uintptr_t)base));
+    mine.offset = (uint64_t)((uintptr_t)local_device - (uintptr_t)base);
+    mine.bytes = block_bytes;
+    std::vector<PeerRecord> all((size_t)c->world);
+    int st = exchange_host(ctx, &mine, sizeof mine, all.data());
+    if (st) return st;
+    for (int p = 0; p < MDIM_MAX_PEERS; ++p) peers[p] = nullptr;
+    for (int p = 0; p < c->world; ++p) {
+        if (p == c->rank) { peers[p] = local_device; continue; }
+        void* mapped = nullptr;
+        for (const Comm::Opened& o : c->opened)
+            if (memcmp(&o.handle, &all[(size_t)p].handle, sizeof o.handle) == 0) mapped = o.base;
+        if (!mapped) {
+            CU(ctx, cudaIpcOpenMemHandle(&mapped, all[(size_t)p].handle, cudaIpcMemLazyEnablePeerAccess));
+            c->opened.push_back({all[(size_t)p].handle, mapped});
+        }
+        peers[p] = (char*)mapped + all[(size_t)p].offset;
+    }
+    return MDIM_OK;
+}
+
+// Collective (contains a barrier: nobody unmaps while a peer may still be reading).
+int mdim_peer_table_close(mdim_ctx* ctx) {
+    if (!ctx || !ctx->comm) return MDIM_ERR_INVALID;
+    int st = mdim_barrier(ctx);
+    if (st) return st;
+    for (const Comm::Opened& o : ctx->comm->opened) CU(ctx, cudaIpcCloseMemHandle(o.base));
+    ctx->comm->opened.clear();
+    return mdim_barrier(ctx);
+}
+
+}  // extern "C"

@@ -37,6 +37,7 @@ const char* status_string(int st) {
         case MDIM_ERR_ARITH: return "integer division by zero or with overflow";
         case MDIM_ERR_INVALID: return "malformed descriptor";
         case MDIM_ERR_NOMEM: return "out of memory";
+        case MDIM_ERR_NCCL: return "NCCL is missing or a collective failed";
     }
     return "unknown status";
 }

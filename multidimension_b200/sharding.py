@@ -12,7 +12,8 @@ The two ops with a real exchange step are
   * a fold over the sharded axis itself: every rank folds its block, then `all_reduce_partial`
     (NCCL all-reduce; f32 order differs from the sequential reference, 1e-6 relative tolerance).
 
-`torch.distributed` is plumbing here and is imported lazily: the package itself does not need torch.
+Nothing here imports torch or torch.distributed: the collectives and the handle exchange go through the C ABI
+(`mdim_comm_init`, `mdim_allgather`, `mdim_allreduce`, `mdim_peer_table`; NCCL inside csrc/comm.cu).
 """
 from __future__ import annotations
 
@@ -94,69 +95,144 @@ class PeerStorage(Storage):
         return self.peers[0]
 
     def close(self):
-        for p in self._opened:
+        for p in self._opened:  # mappings made with mdim_ipc_open directly; a Comm's peer table is closed by Comm.close_peers()
             self.ctx.ipc_close(p)
         self._opened = []
 
 
-def peer_source(local_block_storage, total_len, ctx=None, group=None):
-    """Collective: exchange CUDA IPC handles of every rank's block (all blocks `equal_block` long, the
-    caller pads the last one) and return a PeerStorage addressing the whole source."""
-    import torch.distributed as dist
-    ctx = ctx or default_context()
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    handle = ctx.ipc_export(local_block_storage.dptr)
-    handles = [None] * world
-    dist.all_gather_object(handles, handle, group=group)
-    peers, opened = [], []
-    for p, h in enumerate(handles):
-        if p == rank:
-            peers.append(local_block_storage.dptr)
+class Comm:
+    """The communicator of the C ABI (`mdim_comm_*`, csrc/comm.cu): NCCL bound to a Context, one process per GPU.
+    Every method is a collective call.  Nothing here touches torch.distributed: the data path of a sharded
+    collect is the library's own (peer-mapped kernels, `mdim_allgather`, `mdim_allreduce`)."""
+
+    def __init__(self, ctx, rank, world, unique_id):
+        import ctypes as C
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        idb = (C.c_uint8 * F.COMM_ID_BYTES).from_buffer_copy(unique_id)
+        ctx.check(ctx.lib.mdim_comm_init(ctx.handle, self.rank, self.world, idb))
+        self._open = True
+
+    @staticmethod
+    def unique_id():
+        """128 bytes made by rank 0 (ncclGetUniqueId); ship them to the other ranks by any means."""
+        import ctypes as C
+        idb = (C.c_uint8 * F.COMM_ID_BYTES)()
+        st = F.lib().mdim_comm_unique_id(idb)
+        if st != F.OK:
+            raise F.MdimError(st, "mdim_comm_unique_id: " + F.lib().mdim_status_string(st).decode())
+        return bytes(idb)
+
+    @staticmethod
+    def from_env(ctx=None, path=None, timeout=300.0):
+        """Rendezvous through a file on the node (every rank of ONE box sees /tmp): rank 0 writes the id, the others
+        wait for it.  RANK / WORLD_SIZE as torchrun sets them; the file name is unique per launch (parent pid)."""
+        import os
+        import time
+        ctx = ctx or default_context()
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        path = path or os.environ.get("MDIM_COMM_FILE") or f"/tmp/mdim_comm_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+        if rank == 0:
+            uid = Comm.unique_id()
+            with open(path + ".tmp", "wb") as f:
+                f.write(uid)
+            os.replace(path + ".tmp", path)
         else:
-            ptr = ctx.ipc_open(h)
-            peers.append(ptr)
-            opened.append(ptr)
-    return PeerStorage(local_block_storage.dtype, total_len, peers, equal_block(total_len, world), keep=local_block_storage, ctx=ctx, opened=opened)
+            t0 = time.time()
+            while not os.path.exists(path):
+                if time.time() - t0 > timeout:
+                    raise F.MdimError(F.ERR_NCCL, f"rendezvous file {path} did not appear")
+                time.sleep(0.01)
+            with open(path, "rb") as f:
+                uid = f.read()
+        comm = Comm(ctx, rank, world, uid)
+        comm.barrier()
+        if rank == 0:
+            try:
+                os.remove(path)
+            except OSError:
+                pass
+        return comm
+
+    def info(self):
+        import ctypes as C
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        self.ctx.check(self.ctx.lib.mdim_comm_info(self.ctx.handle, C.byref(r), C.byref(w), C.byref(v)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value}
+
+    def barrier(self):
+        self.ctx.check(self.ctx.lib.mdim_barrier(self.ctx.handle))
+
+    def all_gather_into(self, full, local):
+        """ncclAllGather of every rank's `local` Storage into `full` (rank-major blocks), asynchronous on the context's stream."""
+        import ctypes as C
+        if full.n != local.n * self.world or full.dtype != local.dtype:
+            raise F.Panic(F.ERR_SIZE, "all_gather: the result must hold world x block elements")
+        self.ctx.check(self.ctx.lib.mdim_allgather(self.ctx.handle, C.c_void_p(local.dptr), C.c_void_p(full.dptr), local.nbytes))
+        return full
+
+    def all_reduce(self, storage, op="sum"):
+        """ncclAllReduce in place, asynchronous on the context's stream."""
+        import ctypes as C
+        code = {"sum": F.ADD, "prod": F.MUL, "min": F.REDUCE_MIN, "max": F.REDUCE_MAX}[op]
+        self.ctx.check(self.ctx.lib.mdim_allreduce(self.ctx.handle, C.c_void_p(storage.dptr), storage.n, storage.dtype, code))
+        return storage
+
+    def peer_table(self, dptr, nbytes):
+        import ctypes as C
+        peers = (C.c_void_p * F.MAX_PEERS)()
+        self.ctx.check(self.ctx.lib.mdim_peer_table(self.ctx.handle, C.c_void_p(dptr), nbytes, peers))
+        return [peers[p] for p in range(self.world)]
+
+    def close_peers(self):
+        self.ctx.check(self.ctx.lib.mdim_peer_table_close(self.ctx.handle))
+
+    def close(self):
+        if self._open:
+            self._open = False
+            self.ctx.check(self.ctx.lib.mdim_comm_destroy(self.ctx.handle))
 
 
-def as_torch(storage):
-    """Zero-copy torch view of a device-resident Storage (for torch.distributed collectives)."""
-    import torch
-    np_dtype = {F.U8: "|u1", F.I32: "<i4", F.U32: "<u4", F.I64: "<i8", F.U64: "<u8", F.F32: "<f4", F.F64: "<f8"}[storage.dtype]
-
-    class _Iface:
-        __cuda_array_interface__ = {"shape": (storage.n,), "typestr": np_dtype, "data": (storage.dptr, False), "version": 2}
-    t = torch.as_tensor(_Iface(), device="cuda")
-    if storage.dtype == F.U64:
-        t = t.view(torch.int64) if t.dtype != torch.int64 else t
-    return t
+def peer_source(local_block_storage, total_len, comm):
+    """Collective: map every rank's block (all blocks `equal_block` long, the caller pads the last one) into this
+    process (`mdim_peer_table`: CUDA IPC handles exchanged over the communicator) and return a PeerStorage
+    addressing the whole source."""
+    peers = comm.peer_table(local_block_storage.dptr, local_block_storage.nbytes)
+    return PeerStorage(local_block_storage.dtype, total_len, peers, equal_block(total_len, comm.world), keep=local_block_storage, ctx=comm.ctx)
 
 
-def all_gather_source(local_block, ctx=None, group=None):
-    """NCCL all-gather of a sharded source into a full replica on every rank (equal blocks).
+def all_gather_source(local_block, comm):
+    """NCCL all-gather of a sharded source into a full replica on every rank (equal blocks), through the C ABI.
     `local_block` is a device-resident Array; returns the full Storage (rank-major blocks)."""
-    import torch
-    import torch.distributed as dist
-    ctx = ctx or default_context()
-    world = dist.get_world_size(group)
     st = local_block.storage
-    full = Storage.device(ctx, st.dtype, st.n * world)
-    dist.all_gather_into_tensor(as_torch(full), as_torch(st), group=group)
-    torch.cuda.current_stream().synchronize()
+    full = Storage.device(comm.ctx, st.dtype, st.n * comm.world)
+    comm.all_gather_into(full, st)
+    comm.ctx.sync()
     return full
 
 
-def all_reduce_partial(partial_storage, op="sum", group=None):
-    """Finish a fold over the sharded axis: NCCL all-reduce of the per-rank partial folds, in place."""
-    import torch
-    import torch.distributed as dist
-    ops = {"sum": dist.ReduceOp.SUM, "prod": dist.ReduceOp.PRODUCT, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX,
-           "band": dist.ReduceOp.BAND, "bor": dist.ReduceOp.BOR, "bxor": dist.ReduceOp.BXOR}
-    if partial_storage.home == "device":
-        t = as_torch(partial_storage)
-        dist.all_reduce(t, op=ops[op], group=group)
-        torch.cuda.current_stream().synchronize()
-    else:  # host-resident partials (gloo): used by the CPU test-suite
-        t = torch.from_numpy(partial_storage.host)
-        dist.all_reduce(t, op=ops[op], group=group)
+def all_reduce_partial(partial_storage, op, comm):
+    """Finish a fold over the sharded axis: NCCL all-reduce of the per-rank partial folds, in place (f32 sums are
+    reassociated: 1e-6 relative tolerance, north star)."""
+    comm.all_reduce(partial_storage, op)
+    comm.ctx.sync()
     return partial_storage
+
+
+# Measured on one 8 x B200 NVSwitch box (profiles/r1_bench_n*_multi_ops.json, profiles/r2_scale_*.json):
+_REMOTE_GATHERS_PER_S = 8.0e9    # uniform-random 4-byte reads of a peer's HBM over NVLink, per GPU (2 GPUs: 7.0e9, 8 GPUs: 1.1e10)
+_LOCAL_GATHERS_PER_S = 44.0e9    # the same reads from the GPU's own HBM (config 3: 2^28 in 6.0 ms)
+_ALLGATHER_IN_BYTES_PER_S = 600.0e9  # NCCL all-gather, bytes arriving per GPU per second (615e9 at 8 GPUs)
+
+
+def choose_compose_route(n_idx_local, src_bytes, world, reuse=1):
+    """How should `idx.compose(src)` run when `src` is sharded over `world` GPUs and this rank holds `n_idx_local`
+    indices?  -> "peer" (the gather kernel reads every element from the GPU that owns it, mdim_node.peer[]) or
+    "allgather" (mdim_allgather the source first, then gather locally).  A cost model over the three measured rates
+    above; `reuse` = how many collects will read the gathered source (the all-gather is paid once).
+    Measured crossover: all-gather first wins at 2 GPUs (7.5 vs 9.6 ms), peer-mapped from 4 GPUs up (8 GPUs: 2.7 vs 6.6 ms)."""
+    if world <= 1:
+        return "local"
+    remote = n_idx_local * (world - 1) / world
+    t_peer = remote / _REMOTE_GATHERS_PER_S + (n_idx_local - remote) / _LOCAL_GATHERS_PER_S
+    t_ag = src_bytes * (world - 1) / world / _ALLGATHER_IN_BYTES_PER_S / max(reuse, 1) + n_idx_local / _LOCAL_GATHERS_PER_S
+    return "peer" if t_peer <= t_ag else "allgather"

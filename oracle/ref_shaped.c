@@ -21,6 +21,15 @@
 #include <stdlib.h>
 #include <stdio.h>
 
+/* The product x * y must be rounded to f32 before the add (Rust never contracts x * y + 1.0 into an FMA).  The default
+ * build forces that with a volatile temporary; the -O3 -march=x86-64-v3 build (libmdim_refshaped_o3.so, the most the
+ * reference could get from `cargo build --release` with the vectoriser on) relies on -ffp-contract=off instead. */
+#ifdef REF_NO_VOLATILE
+#define SEPARATELY_ROUNDED float
+#else
+#define SEPARATELY_ROUNDED volatile float
+#endif
+
 typedef struct { float* ptr; uint64_t len, cap; } vec_f32;
 
 static void grow(vec_f32* v) { /* never reached: capacity is exact, as with Vec::with_capacity */
@@ -46,7 +55,7 @@ int ref_c2_zip_map(const float* a, const float* b, uint64_t n, float* out) {
         float x = a[i];
         CHECK(i, n); CHECK(i, n);          /* operand b */
         float y = b[i];
-        volatile float m = x * y;          /* separately rounded */
+        SEPARATELY_ROUNDED m = x * y;          /* separately rounded */
         push(&v, m + 1.0f);
     }
     return v.len == n ? 0 : 2;             /* Array::new_inner assert, src/array.rs:12 */
@@ -128,7 +137,7 @@ int ref_c5_chain(const float* a, uint64_t P, uint64_t Q, const float* w, uint64_
                             x = a[k];
                         }
                         CHECK(r, R); CHECK(r, R);
-                        volatile float m = x * w[r];
+                        SEPARATELY_ROUNDED m = x * w[r];
                         push(&v, m + 1.0f);
                     }
     return v.len == Q * P * Q * P * R ? 0 : 2;

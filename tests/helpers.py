@@ -124,10 +124,12 @@ def assert_same_bits(got, want, what=""):
         raise AssertionError(f"{what}: {bad.size} of {got.size} elements differ; first at {k}: got {got[k]!r}, want {want[k]!r}")
 
 
-def refshaped_lib():
-    """oracle/ref_shaped.c: the five BASELINE configs as rustc-shaped monomorphic loops (CPU baseline)."""
-    if "ref" not in _libs:
-        path = os.path.join(ORACLE_DIR, "_build", "libmdim_refshaped.so")
+def refshaped_lib(variant=""):
+    """oracle/ref_shaped.c: the five BASELINE configs as rustc-shaped monomorphic loops (CPU baseline).
+    variant "" = -O2 -fno-tree-vectorize (README: "not SIMD optimized"); "_o3" = -O3 -march=x86-64-v3, vectoriser on."""
+    key = "ref" + variant
+    if key not in _libs:
+        path = os.path.join(ORACLE_DIR, "_build", f"libmdim_refshaped{variant}.so")
         if not os.path.exists(path):
             subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
         lib = C.CDLL(path)
@@ -140,5 +142,5 @@ def refshaped_lib():
         lib.ref_c5_chain.argtypes = [P_, U, U, P_, U, P_]
         for f in ("ref_c2_zip_map", "ref_c1_transpose", "ref_c3_compose", "ref_c4_fold", "ref_c4_sub", "ref_c5_chain"):
             getattr(lib, f).restype = C.c_int
-        _libs["ref"] = lib
-    return _libs["ref"]
+        _libs[key] = lib
+    return _libs[key]

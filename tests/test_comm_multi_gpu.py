@@ -1,0 +1,61 @@
+"""The multi-GPU surface of the C ABI on real GPUs (>= 2 needed; skipped otherwise): one process per GPU, every
+exchange through include/mdim.h — no torch.distributed anywhere.  Run with `gpurun --gpus 2 -- python -m pytest
+tests/test_comm_multi_gpu.py -m gpu`."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import assert_same_bits
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_c_abi_collectives_and_peer_tables(world, tmp_path):
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    rdv = str(tmp_path / "rendezvous")
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "multi", "comm_worker.py"), str(r), str(world), rdv, str(tmp_path)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o[-3000:]}"
+    parts = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
+    rng = np.random.default_rng(2024)
+    n_src = 1 << 16
+    src = rng.uniform(-1, 1, n_src).astype(np.float32)
+    idx = rng.integers(0, n_src, 5000).astype(np.uint64)
+    want = src[idx.astype(np.int64)]
+    assert_same_bits(np.concatenate([p["ag_gather"] for p in parts]), want, "all-gather + gather")
+    assert_same_bits(np.concatenate([p["peer_gather"] for p in parts]), want, "peer-mapped gather (block at an interior offset)")
+    M, N = 64 * world * 2, 384
+    mat = rng.uniform(-1, 1, M * N).astype(np.float32)
+    assert_same_bits(np.concatenate([p["peer_transpose"] for p in parts]), mat.reshape(M, N).T.copy().reshape(-1), "peer-mapped transpose")
+    assert_same_bits(np.concatenate([p["peer_transpose_notma"] for p in parts]), mat.reshape(M, N).T.copy().reshape(-1), "peer-mapped transpose (evaluator)")
+    assert "transpose" in bytes(parts[0]["peer_transpose_kernel"]).decode()
+    I, J, K = 16 * world, 24, 32
+    a = rng.uniform(0, 1, I * J * K).astype(np.float32)
+    seq = np.zeros(J * K, np.float32)
+    for i in range(I):
+        seq = seq + a.reshape(I, J * K)[i]
+    for p in parts:  # reassociated across ranks: the north star's 1e-6 relative tolerance
+        assert np.max(np.abs(p["fold_allreduce"] - seq) / np.abs(seq)) <= 1e-6
+    assert_same_bits(np.concatenate([p["fold_exact"] for p in parts]), seq, "peer-mapped fold over the sharded axis (bit-exact)")
+    ranks = np.arange(world)
+    for p in parts:
+        assert p["ar_sum"].tolist() == [int((ranks + 1).sum()), int((10 - ranks).sum()), 7 * world]
+        assert p["ar_prod"].tolist() == [int(np.prod(ranks + 1)), int(np.prod(10 - ranks)), 7 ** world]
+        assert p["ar_min"].tolist() == [1, 10 - (world - 1), 7]
+        assert p["ar_max"].tolist() == [world, 10, 7]

@@ -215,7 +215,6 @@ def _free_port():
 def _worker(rank, world, port, out_dir):
     import torch
     import torch.distributed as dist
-    from multidimension_b200.sharding import all_reduce_partial
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -236,7 +235,7 @@ def _worker(rank, world, port, out_dir):
     At = A.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize))  # (J,K) x local I
     part = emu_collect(fold_rows(At, (usize, usize), usize, Add, np.float32(0)))
     st = Storage.from_host(F.F32, part.copy())
-    all_reduce_partial(st, "sum")
+    dist.all_reduce(torch.from_numpy(st.host))  # gloo stands in for mdim_allreduce (NCCL, GPU only): same per-rank flow
     # (4) compose with a sharded source: all-gather the source, gather locally (index shard per rank)
     src_block = torch.from_numpy(a[rank * (a.size // world):(rank + 1) * (a.size // world)].copy())
     gathered = [torch.empty_like(src_block) for _ in range(world)]
