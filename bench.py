@@ -398,6 +398,7 @@ def main():
     clocks.start()
     ms_step, launches = B.time_launches(lambda: view.collect(out=st_out, flags=F.COLLECT_ASYNC), args.steps, args.warmup)
     clocks.stop()
+    kernel_ran = ctx.last_kernel()
     alg_bytes = 12 * n
     per_gpu = alg_bytes / (ms_step * 1e-3) / 1e9
     value = per_gpu * world
@@ -415,7 +416,7 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
                      "frac_of_nominal_8000": per_gpu / 8000.0, "peak_source": peak_src,
-                     "kernel": "k_eval<SigMulAddCF32, u32, V=8, R1>", "traffic": known_traffic("k_eval_SigMulAddCF32"),
+                     "kernel": "k_eval<SigMulAddCF32, u32, V=8, R1>", "kernel_ran": kernel_ran, "traffic": known_traffic("k_eval_SigMulAddCF32"),
                      "traffic_source": TRAFFIC_SOURCE},
     }
 
@@ -532,7 +533,7 @@ def bench_ops(B, ta, tout):
     def line(name, alg_bytes, ms, plan, **extra):
         gbs = alg_bytes / (ms * 1e-3) / 1e9
         ops[name] = dict({"GB/s": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 4), "frac_of_nominal_8000": round(gbs / 8000.0, 4),
-                          "ms": round(ms, 5), "algorithmic_bytes": alg_bytes, "kernel": plan}, **extra)
+                          "ms": round(ms, 5), "algorithmic_bytes": alg_bytes, "kernel": plan, "kernel_ran": ctx.last_kernel()}, **extra)
 
     # C1: 4096x4096 f32 transpose; 16 rotating source/destination pairs (2 GiB) keep it out of L2
     R = 16
@@ -660,7 +661,7 @@ def bench_scaling_ops(B, ta, tout):
     def row(name, alg_bytes, ms, n1_ms, kernel, nvlink_in_bytes=0, **extra):
         gbs = alg_bytes / (ms * 1e-3) / 1e9
         r = {"ms": round(ms, 5), "GB/s": round(gbs, 1), "n1_ms": round(n1_ms, 5), "speedup_vs_n1": round(n1_ms / ms, 3),
-             "frac_of_measured_peak": round(gbs / (peak * world), 4), "algorithmic_bytes": alg_bytes, "kernel": kernel}
+             "frac_of_measured_peak": round(gbs / (peak * world), 4), "algorithmic_bytes": alg_bytes, "kernel": kernel, "kernel_ran": ctx.last_kernel()}
         if nvlink_in_bytes:
             r["nvlink_in_gbs_per_gpu"] = round(nvlink_in_bytes / (ms * 1e-3) / 1e9, 1)
         r.update(extra)

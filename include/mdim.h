@@ -196,6 +196,12 @@ int mdim_sync(mdim_ctx* ctx); /* waits for the stream; returns the deferred stat
 int mdim_last_error(mdim_ctx* ctx, mdim_error_info* info);
 const char* mdim_status_string(int status);
 uint64_t mdim_launch_count(mdim_ctx* ctx); /* kernels launched by this library so far */
+/* The kernel the LAST collect launched: a pre-built one ("k_eval<SigMulAddCF32>...", "k_transpose_tma", "k_fold_regs"), or
+ * "mdim_jit_kernel[ops]" / "mdim_jit_kernel[ops+shape]" when the chain was specialised at run time.
+ * NVRTC (libnvrtc, part of the CUDA toolkit) is OPTIONAL: without it, or with MDIM_COLLECT_NO_JIT, chains outside the
+ * pre-built signature table run through the depth-specialised interpreter of the same evaluator (about 0.3x of the
+ * specialised rate), and rank >= 2 chains keep run-time strides (config 5: 0.61 instead of 0.93 of 8 TB/s). */
+int mdim_last_kernel(mdim_ctx* ctx, char* buf, size_t buf_len);
 int mdim_device_info(mdim_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes);
 
 /* ---- device-resident boxed buffer: the `Box<[T]>` of Array (src/array.rs:5-8) ------------------ */

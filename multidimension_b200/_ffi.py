@@ -76,6 +76,7 @@ SYMBOLS = [
     ("mdim_last_error", C.c_int, [_P, C.POINTER(ErrorInfo)]),
     ("mdim_status_string", C.c_char_p, [C.c_int]),
     ("mdim_launch_count", C.c_uint64, [_P]),
+    ("mdim_last_kernel", C.c_int, [_P, C.c_char_p, C.c_size_t]),
     ("mdim_device_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     ("mdim_buf_alloc", C.c_int, [_P, C.c_size_t, _PP]),
     ("mdim_buf_free", C.c_int, [_P, _P]),

@@ -120,7 +120,9 @@ int launch_eval(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err, bool expl
     int grid;
     // an op tree without a pre-built signature is specialised on first use (jit.cu); else the interpreter runs
     void* jit = nullptr;
-    if (!(p.flags & (MDIM_COLLECT_NO_STATIC | MDIM_COLLECT_NO_JIT))) jit = jit_kernel_for(p);
+    int jit_level = 0;
+    if (!(p.flags & (MDIM_COLLECT_NO_STATIC | MDIM_COLLECT_NO_JIT))) jit = jit_kernel_for(p, &jit_level);
+    snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "%s", jit ? (jit_level == 2 ? "mdim_jit_kernel[ops+shape]" : "mdim_jit_kernel[ops]") : v->name);
     Program q = p.prog;
     static const bool no256 = [] { const char* e = getenv("MDIM_NO_VEC256"); return e && e[0] == '1'; }();
     if (p.vec256_ok && !no256 && ((uintptr_t)out % 32) == 0) q.flags |= PF_VEC256;
@@ -163,7 +165,7 @@ int launch_plan(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err) {
             const int grid = (int)std::min<uint64_t>(p.tr.n_tiles, std::max<uint64_t>(cap, 1));
             TransposePlan tr = p.tr;
             tr.nowait = nowait;
-            launch_transpose(tr, out, grid, ctx->stream);
+            snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "%s", launch_transpose(tr, out, grid, ctx->stream));
             ctx->launches++;
             CU(ctx, cudaGetLastError());
             return MDIM_OK;
@@ -171,7 +173,7 @@ int launch_plan(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err) {
         case KK_FOLD_ROWS: {
             FoldRowsPlan fr = p.fr;
             fr.nowait = nowait;
-            launch_fold_rows(fr, out, ctx->sm_count, ctx->stream);
+            snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "%s", launch_fold_rows(fr, out, ctx->sm_count, ctx->stream));
             ctx->launches++;
             CU(ctx, cudaGetLastError());
             return MDIM_OK;
@@ -325,6 +327,12 @@ int mdim_set_stream(mdim_ctx* ctx, void* cuda_stream) {
 int mdim_get_stream(mdim_ctx* ctx, void** cuda_stream) {
     if (!ctx || !cuda_stream) return MDIM_ERR_INVALID;
     *cuda_stream = (void*)ctx->stream;
+    return MDIM_OK;
+}
+
+int mdim_last_kernel(mdim_ctx* ctx, char* buf, size_t buf_len) {
+    if (!ctx || !buf || !buf_len) return MDIM_ERR_INVALID;
+    snprintf(buf, buf_len, "%s", ctx->last_kernel);
     return MDIM_OK;
 }
 

@@ -53,6 +53,7 @@ struct mdim_ctx {
     bool dep_tracking = true;  // MDIM_DEP_TRACK=0: every kernel waits (round-1 behaviour)
     size_t host_chunk_bytes = 128u << 20;  // measured: 8 MB 60.7, 32 MB 73.1, 128 MB 75.8, 512 MB 76.3 GB/s end to end
     mdim::Comm* comm = nullptr;  // mdim_comm_init (comm.cu)
+    char last_kernel[96] = {0};  // mdim_last_kernel: what the last collect actually launched
 };
 
 namespace mdim {

@@ -259,7 +259,8 @@ int jit_compile_check(const Plan& p, char* log, size_t log_len) {
 //   level 2: the op sequence AND the shape — strides, lengths, dividers and predicates become immediates.
 //            Built when the same (ops, shape) has been collected MDIM_JIT_SHAPES times (default 2; 0 = never,
 //            1 = at once) and the chain is a rank >= 2 evaluator plan, where the coordinate decode dominates.
-void* jit_kernel_for(const Plan& p) {
+void* jit_kernel_for(const Plan& p, int* level) {
+    if (level) *level = 0;
     static const bool enabled = [] { const char* e = getenv("MDIM_JIT"); return !(e && e[0] == '0'); }();
     static const int shape_after = [] { const char* e = getenv("MDIM_JIT_SHAPES"); return e ? atoi(e) : 2; }();
     if (!enabled || (p.kind != KK_STREAM && p.kind != KK_GENERIC) || p.vpt != 1) return nullptr;
@@ -297,11 +298,13 @@ void* jit_kernel_for(const Plan& p) {
         const std::string skey = key + "#" + shape_key(p.prog);
         if (seen.size() > 4096) seen.clear();  // a workload of ever-changing shapes must not grow this without bound
         if (++seen[skey] >= shape_after) {
-            if (void* k = build(cache()[skey], true)) return k;
+            if (void* k = build(cache()[skey], true)) { if (level) *level = 2; return k; }
         }
     }
     if (p.static_id >= 0) return nullptr;  // the pre-built signature serves it
-    return build(cache()[key], false);
+    void* k = build(cache()[key], false);
+    if (k && level) *level = 1;
+    return k;
 }
 
 }  // namespace mdim

@@ -334,7 +334,7 @@ template <bool FAST> static bool launch_regs(const FoldRowsPlan& R, void* out, c
 
 }  // namespace
 
-void launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream_t stream) {
+const char* launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream_t stream) {
     static const int env_warps = [] { const char* e = getenv("MDIM_FOLD_WARPS"); return e ? atoi(e) : 0; }();
     static const int env_stages = [] { const char* e = getenv("MDIM_FOLD_STAGES"); return e ? atoi(e) : 0; }();
     // column chunk: the whole row when a 32-row tile of it fits 64 KB (and always for the fused form,
@@ -369,7 +369,7 @@ void launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream
     // the TMA / shared-memory form for the fold alone (config 4a: 6.28 vs 5.66 TB/s).
     static const int mode = [] { const char* e = getenv("MDIM_FOLD_MODE"); return e ? atoi(e) : 0; }();  // 1 = always smem, 2 = always registers
     const bool want_regs = mode == 2 || (mode == 0 && R.epilogue != 0);
-    if (want_regs && (fast ? launch_regs<true>(R, out, stream) : launch_regs<false>(R, out, stream))) return;
+    if (want_regs && (fast ? launch_regs<true>(R, out, stream) : launch_regs<false>(R, out, stream))) return "k_fold_regs";
     // i / q4 for the flat epilogue walk: umulhi(i, mul) >> shr, exact for i < 2^31 (q4 >= 2 here)
     uint32_t q4 = (uint32_t)ch / 4, lg = 0;
     while ((1u << lg) < q4) ++lg;
@@ -380,6 +380,7 @@ void launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream
         launch_pdl(kern, dim3(grid), dim3(kFoldThreads), smem, stream, R, out, n_warps, stages, ch, skew, q4_mul, q4_shr);
     };
     if (fast) go(k_fold_rows<true>); else go(k_fold_rows<false>);
+    return "k_fold_rows";
 }
 
 }  // namespace mdim

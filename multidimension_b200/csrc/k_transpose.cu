@@ -510,23 +510,24 @@ static bool launch_transpose_tma(const TransposePlan& T, void* out, cudaStream_t
 // equal at 16384^2 (6.31 vs 6.32 TB/s) and slower at 4096^2 (5.25 vs 5.67), as are 32 x 64 and 16 x 128 (5.1 TB/s).
 #define MDIM_TR_SHAPES(X) X(16, 64) X(32, 128)
 
-void launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t stream) {
-    if (launch_transpose_tma(T, out, stream)) return;
+const char* launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t stream) {
+    if (launch_transpose_tma(T, out, stream)) return T.n_peers > 1 ? "k_transpose_tma<peer>" : "k_transpose_tma";
     const bool vec = transpose_vec_ok(T, out);
     if (vec && use_pipe() && T.tile_ac == 16 && T.tile_b == 64 && T.n_peers <= 1) {
         constexpr int smem = kTrStages * 64 * 64 * 4;
         if (T.esize == 4) launch_pdl(k_transpose_pipe<4>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);
         else launch_pdl(k_transpose_pipe<8>, dim3(grid), dim3(kTrThreads), smem, stream, T, out);
-        return;
+        return "k_transpose_pipe";
     }
 #define X(AC, B)                                                                      \
     if (T.tile_ac == AC && T.tile_b == B) {                                           \
         if (T.esize == 4) launch_tr<4, AC, B>(T, out, grid, vec, stream);             \
         else launch_tr<8, AC, B>(T, out, grid, vec, stream);                          \
-        return;                                                                       \
+        return vec ? "k_transpose<regs,vec>" : "k_transpose<regs,scalar>";            \
     }
     MDIM_TR_SHAPES(X)
 #undef X
+    return "k_transpose<none>";
 }
 
 }  // namespace mdim

@@ -46,12 +46,12 @@ const EvalVariant* eval_variants_s64_static(int* n);
 // K2: tiled transpose of one leaf (see k_transpose.cu)
 // ------------------------------------------------------------------------------------------------
 constexpr int kTrThreads = 256;
-void launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t stream);
+const char* launch_transpose(const TransposePlan& T, void* out, int grid, cudaStream_t stream);  // -> name of the kernel launched
 
 // ------------------------------------------------------------------------------------------------
 // K4: sequential-order last-axis fold, optionally fused with a broadcast epilogue (k_fold.cu)
 // ------------------------------------------------------------------------------------------------
 constexpr int kFoldThreads = 256;
-void launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream_t stream);
+const char* launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream_t stream);  // -> name of the kernel launched
 
 }  // namespace mdim

@@ -55,6 +55,12 @@ class Context:
     def sync(self):
         self.check(self.lib.mdim_sync(self.handle))
 
+    def last_kernel(self):
+        """Name of the kernel the last collect launched (`mdim_jit_kernel[ops+shape]` when NVRTC specialised the chain)."""
+        buf = C.create_string_buffer(96)
+        self.check(self.lib.mdim_last_kernel(self.handle, buf, 96))
+        return buf.value.decode()
+
     def launch_count(self):
         return int(self.lib.mdim_launch_count(self.handle))
 
