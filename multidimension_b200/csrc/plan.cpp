@@ -715,6 +715,14 @@ int plan_expr(const mdim_expr* e, uint32_t flags, Plan* plan, char* why_buf, siz
         delete b; return MDIM_OK;
     }
     input_ranges(e, plan);
+    bool gather_big = false;
+    for (int i = 0; i < e->n_nodes; ++i) {
+        const mdim_node& n = e->nodes[i];
+        if (n.kind != MDIM_NODE_GATHER || n.n_peers > 1) continue;
+        uint64_t span = 1;
+        for (int c = 0; c < n.n_comp; ++c) span += (uint64_t)(n.gstride[c] < 0 ? -n.gstride[c] : n.gstride[c]) * (n.bound[c] ? n.bound[c] - 1 : 0);
+        if (span * (uint64_t)dtype_size(n.dtype) > kGatherBigBytes) gather_big = true;
+    }
     if (flags & kPlanScalarOut) b->force_vec = 1;
     b->canonical_axes();
     st = b->emit();
@@ -742,6 +750,7 @@ int plan_expr(const mdim_expr* e, uint32_t flags, Plan* plan, char* why_buf, siz
         st = b->detect_fast_paths();
         if (st) { delete b; return st; }
     }
+    if (gather_big) plan->prog.flags |= PF_GATHER_BIG;
     delete b;
     return MDIM_OK;
 }

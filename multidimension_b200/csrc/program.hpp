@@ -77,6 +77,7 @@ struct PeerTab {
 enum ProgFlags : uint32_t {
     PF_EXPLAIN = 1u,  // single-lane rerun that records mdim_error_info details
     PF_VEC256 = 2u,   // every vector operand and the output are 32-byte aligned: 256-bit loads / stores
+    PF_GATHER_BIG = 8u,  // a gathered source spans more than kGatherBigBytes: 64-byte L2 fetches (exec.cuh: ld32_big)
     PF_NOWAIT = 4u,   // no buffer of this launch is touched by a kernel still in flight: skip griddepcontrol.wait (launch.cuh)
 };
 
@@ -168,6 +169,7 @@ struct FoldRowsPlan {
 };
 
 // Memory a launch reads (api.cu adds the output and decides whether the kernel may skip griddepcontrol.wait).
+constexpr uint64_t kGatherBigBytes = 1ull << 30;  // ~8x the 126 MB L2: below that the plain load's L2 hits win (probe)
 constexpr int kMaxRanges = 24;
 struct MemRange { uint64_t lo, hi; };  // [lo, hi) bytes
 
