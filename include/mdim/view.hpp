@@ -15,6 +15,7 @@
 //   a.rows::<I,J>().map(|r| fold r.each(..))     a.rows<I, J>().fold<Add>(init)       (sequential, index order)
 //   v.collect::<Array<I,T>>()                    v.collect(executor)
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -39,10 +40,14 @@ struct Panic : std::runtime_error {
 };
 struct Unsupported : std::runtime_error { using std::runtime_error::runtime_error; };
 
-// ---- index types (src/index.rs, src/int.rs): usize, bool, Unit = (), Fixed<N>, std::tuple<I...> ------
+// ---- index types (src/index.rs, src/int.rs): usize, bool, Unit = (), Fixed<N>, Reversed, Option<I>, std::tuple<I...> ------
 using usize = uint64_t;
 using Unit = std::tuple<>;
 template <size_t N> struct Fixed { uint64_t v; };
+struct Reversed { uint64_t v; };                       // src/int.rs:58-86: counts backwards, position = size - 1 - v
+template <class I> struct Option { bool some; I value; };  // src/index.rs:244-276: None is position 0, Some(i) is 1 + i.to_usize()
+template <class I> Option<I> None() { return Option<I>{false, I{}}; }
+template <class I> Option<I> Some(const I& i) { return Option<I>{true, i}; }
 
 template <class I> struct Ix;  // Size type, flattened leaf-type list, position-axis lengths
 template <> struct Ix<usize> {
@@ -67,7 +72,21 @@ template <size_t N> struct Ix<Fixed<N>> {  // src/int.rs:33-54
     static void lengths(const Size&, std::vector<uint64_t>& out) { out.push_back(N); }
     static void flat_size(const Size&, std::vector<uint64_t>&) {}
     static Size build(const uint64_t*&) { return {}; }
-    static void positions(const Fixed<N>& i, const Size&, std::vector<uint64_t>& out) { out.push_back(i.v); }
+    static void positions(const Fixed<N>& i, const Size&, std::vector<uint64_t>& out) {
+        // Fixed::to_usize is unchecked (src/int.rs:44); the slice access items[to_usize] is what panics (src/array.rs:86)
+        if (!(i.v < N)) throw Panic(MDIM_ERR_OOB, "Index " + std::to_string(i.v) + " is out of bounds for size " + std::to_string(N));
+        out.push_back(i.v);
+    }
+};
+template <> struct Ix<Reversed> {  // src/int.rs:58-86
+    using Size = uint64_t; using Flat = std::tuple<Reversed>;
+    static void lengths(const Size& s, std::vector<uint64_t>& out) { out.push_back(s); }
+    static void flat_size(const Size& s, std::vector<uint64_t>& out) { out.push_back(s); }
+    static Size build(const uint64_t*& it) { return *it++; }
+    static void positions(const Reversed& i, const Size& s, std::vector<uint64_t>& out) {
+        if (!(i.v < s)) throw Panic(MDIM_ERR_OOB, "Index " + std::to_string(i.v) + " is out of bounds for size " + std::to_string(s));
+        out.push_back(s - 1 - i.v);
+    }
 };
 template <class... Is> struct Ix<std::tuple<Is...>> {  // src/index.rs:75-154; arity <= 3 (src/tuple.rs:92-145)
     static_assert(sizeof...(Is) <= 3, "tuple index types have arity <= 3 in the reference");
@@ -85,6 +104,19 @@ template <class... Is> struct Ix<std::tuple<Is...>> {  // src/index.rs:75-154; a
     template <size_t... K> static void pos(const std::tuple<Is...>& i, const Size& s, std::vector<uint64_t>& out, std::index_sequence<K...>) {
         (void)i; (void)s; (void)out;
         (Ix<Is>::positions(std::get<K>(i), std::get<K>(s), out), ...);
+    }
+};
+template <class I> struct Ix<Option<I>> {  // one position axis: [None, Some(0), Some(1), ...] (src/index.rs:248)
+    using Size = typename Ix<I>::Size; using Flat = std::tuple<Option<I>>;
+    static uint64_t inner_length(const Size& s) { std::vector<uint64_t> l; Ix<I>::lengths(s, l); uint64_t n = 1; for (uint64_t x : l) n *= x; return n; }
+    static void lengths(const Size& s, std::vector<uint64_t>& out) { out.push_back(1 + inner_length(s)); }
+    static void flat_size(const Size& s, std::vector<uint64_t>& out) { Ix<I>::flat_size(s, out); }
+    static Size build(const uint64_t*& it) { return Ix<I>::build(it); }
+    static void positions(const Option<I>& i, const Size& s, std::vector<uint64_t>& out) {
+        if (!i.some) { out.push_back(0); return; }
+        std::vector<uint64_t> p, l; Ix<I>::positions(i.value, s, p); Ix<I>::lengths(s, l);
+        uint64_t k = 0; for (size_t a = 0; a < p.size(); ++a) k = k * l[a] + p[a];
+        out.push_back(1 + k);
     }
 };
 template <class I> using SizeOf = typename Ix<I>::Size;
@@ -137,10 +169,12 @@ struct Node {
     std::vector<std::pair<AxisP, int64_t>> stride;
     std::vector<int64_t> gstride;
     std::vector<uint64_t> bound;
-    struct Pair { AxisP a, b; uint64_t c; };  // coord[a] == coord[b], or == c when !b
+    struct Pair { AxisP a, b; uint64_t c; int64_t off = 0; };  // coord[a] == coord[b] + off, or == c when !b
     std::vector<Pair> pairs;
     mdim_scalar imm{};
     std::vector<AxisP> red_axes;
+    std::vector<const void*> peers;  // LEAF / GATHER: the Array is cut into equal blocks of peer_block elements, block p at peers[p]
+    uint64_t peer_block = 0;         // (the other GPUs' HBM, mapped with mdim_peer_table; read over NVLink inside the kernel)
 };
 using Groups = std::vector<std::vector<AxisP>>;
 struct Sub_ { int64_t constant = 0; std::vector<std::pair<AxisP, int64_t>> terms; };
@@ -161,22 +195,25 @@ inline NodeP substitute(const NodeP& n, const Table& t) {
         out->stride.clear();
         for (auto& e : st) if (e.second != 0) out->stride.push_back(e);
     } else if (n->kind == MDIM_NODE_DIAG) {
-        auto side = [&](const AxisP& a, uint64_t c, AxisP& oa, uint64_t& oc) {
-            oa = a; oc = c;
-            if (!a) return;
-            if (const Sub_* sub = lookup(t, a)) {
-                if (sub->terms.empty()) { oa = nullptr; oc = (uint64_t)sub->constant; }
-                else if (sub->terms.size() == 1 && sub->terms[0].second == 1 && sub->constant == 0) oa = sub->terms[0].first;
-                else throw Unsupported("a Diagonal whose axis has been split needs device div/mod");
+        // each side is (axis | none, constant): coord[a] + ca == coord[b] + cb   (lowering.py::substitute)
+        auto side = [&](const AxisP& x, int64_t c, AxisP& ox, int64_t& oc) {
+            ox = x; oc = c;
+            if (!x) return;
+            if (const Sub_* sub = lookup(t, x)) {
+                if (sub->terms.empty()) { ox = nullptr; oc = c + sub->constant; }
+                else if (sub->terms.size() == 1 && sub->terms[0].second == 1) { ox = sub->terms[0].first; oc = c + sub->constant; }
+                else throw Unsupported("a Diagonal whose axis has been split or merged needs device div/mod");
             }
         };
         std::vector<Node::Pair> ps; bool dead = false;
         for (auto& p : n->pairs) {
-            AxisP a, b; uint64_t ca = 0, cb = 0;
-            side(p.a, 0, a, ca); side(p.b, p.c, b, cb);
+            AxisP a, b; int64_t ca = 0, cb = 0;
+            side(p.a, 0, a, ca);
+            side(p.b, p.b ? p.off : (int64_t)p.c, b, cb);
             if (!a && !b) { if (ca != cb) dead = true; continue; }
-            if (!a) { std::swap(a, b); std::swap(ca, cb); }
-            ps.push_back({a, b, cb});
+            if (!a) { std::swap(a, b); std::swap(ca, cb); }  // constant == coord[b] + cb  ->  coord[b] == constant - cb
+            if (!b) { const int64_t k = cb - ca; if (k < 0) { dead = true; continue; } ps.push_back({a, nullptr, (uint64_t)k, 0}); }
+            else ps.push_back({a, b, 0, cb - ca});
         }
         if (dead) { auto c = std::make_shared<Node>(); c->kind = MDIM_NODE_CONST; c->dtype = n->dtype; c->imm = n->imm; return c; }
         if (ps.empty()) return out->kids[0];
@@ -186,7 +223,7 @@ inline NodeP substitute(const NodeP& n, const Table& t) {
             const int64_t thr = (int64_t)n->pairs[0].c;
             if (sub->terms.empty()) return sub->constant < thr ? out->kids[0] : out->kids[1];  // pinned (row/column): one side survives
             if (sub->terms.size() == 1 && sub->terms[0].second == 1)  // k = k' + c:  k < thr  <=>  k' < thr - c
-                out->pairs[0] = {sub->terms[0].first, nullptr, (uint64_t)std::max<int64_t>(thr - sub->constant, 0)};
+                out->pairs[0] = {sub->terms[0].first, nullptr, (uint64_t)std::max<int64_t>(thr - sub->constant, 0), 0};
             else throw Unsupported("a Concat whose axis has been split needs device div/mod");
         }
     } else if (n->kind == MDIM_NODE_FOLD) {
@@ -195,6 +232,49 @@ inline NodeP substitute(const NodeP& n, const Table& t) {
     return out;
 }
 inline Sub_ rename_to(const AxisP& b) { Sub_ s; s.terms.push_back({b, 1}); return s; }
+// Row-major combination of the pieces an axis has been cut into (outermost first); unit pieces carry no term.
+inline Sub_ sub_of(const std::vector<AxisP>& pieces) {
+    Sub_ s; int64_t acc = 1;
+    for (auto it = pieces.rbegin(); it != pieces.rend(); ++it) { if ((*it)->length != 1) s.terms.push_back({*it, acc}); acc *= (int64_t)(*it)->length; }
+    return s;
+}
+// Common refinement of two row-major factorisations of the same run of positions (multidimension_b200/view.py::_refine):
+// an axis merged by to_usize out of (2, 3) against a plain axis of 6, or (2, 6) against (4, 3).
+inline void refine(const std::vector<uint64_t>& a, const std::vector<uint64_t>& b, std::vector<uint64_t>& pieces, std::vector<std::vector<size_t>>& ma,
+                   std::vector<std::vector<size_t>>& mb) {
+    for (uint64_t x : a) if (x == 0) throw Unsupported("re-splitting an empty axis");
+    for (uint64_t x : b) if (x == 0) throw Unsupported("re-splitting an empty axis");
+    pieces.clear(); ma.assign(a.size(), {}); mb.assign(b.size(), {});
+    size_t i = 0, j = 0; uint64_t ra = 0, rb = 0;  // 0 = not loaded
+    for (;;) {
+        while (!ra && i < a.size()) { if (a[i] == 1) { ma[i].push_back(pieces.size()); pieces.push_back(1); ++i; } else ra = a[i]; }
+        while (!rb && j < b.size()) { if (b[j] == 1) { mb[j].push_back(pieces.size()); pieces.push_back(1); ++j; } else rb = b[j]; }
+        if (!ra || !rb) break;
+        uint64_t step;
+        if (ra % rb == 0) step = rb; else if (rb % ra == 0) step = ra;
+        else throw Unsupported("axis groups have no common refinement: this remapping needs div/mod on the device");
+        ma[i].push_back(pieces.size()); mb[j].push_back(pieces.size()); pieces.push_back(step);
+        ra /= step; rb /= step;
+        if (ra == 1) { ++i; ra = 0; }
+        if (rb == 1) { ++j; rb = 0; }
+    }
+    if (ra || rb) throw Unsupported("axis groups do not describe the same run of positions");
+}
+// One leaf axis seen by both operands of a binary / concat as the groups a (self) and b (other): -> the group of the result.
+inline std::vector<AxisP> unify_group(const std::vector<AxisP>& a, const std::vector<AxisP>& b, Table& tv, Table& tw) {
+    std::vector<uint64_t> la, lb;
+    for (auto& x : a) la.push_back(x->length);
+    for (auto& y : b) lb.push_back(y->length);
+    if (la == lb) { for (size_t k = 0; k < a.size(); ++k) tw.push_back({b[k].get(), rename_to(a[k])}); return a; }
+    std::vector<uint64_t> pieces; std::vector<std::vector<size_t>> ma, mb;
+    refine(la, lb, pieces, ma, mb);
+    std::vector<AxisP> axes;
+    for (uint64_t n : pieces) axes.push_back(std::make_shared<Axis>(Axis{n}));
+    auto pick = [&](const std::vector<size_t>& idx) { std::vector<AxisP> o; for (size_t k : idx) o.push_back(axes[k]); return o; };
+    for (size_t k = 0; k < a.size(); ++k) tv.push_back({a[k].get(), sub_of(pick(ma[k]))});
+    for (size_t k = 0; k < b.size(); ++k) tw.push_back({b[k].get(), sub_of(pick(mb[k]))});
+    return axes;
+}
 inline Sub_ pin_at(uint64_t c) { Sub_ s; s.constant = (int64_t)c; return s; }
 inline std::vector<AxisP> flat(const Groups& g) { std::vector<AxisP> o; for (auto& x : g) o.insert(o.end(), x.begin(), x.end()); return o; }
 template <class I> Groups fresh_groups(const SizeOf<I>& s) {
@@ -235,12 +315,17 @@ inline void emit_and_run(const NodeP& root, const std::vector<AxisP>& axes, cons
         const Node& n = *order[i]; mdim_node& d = nodes[i];
         std::memset(&d, 0, sizeof d);
         d.kind = n.kind; d.dtype = n.dtype; d.op = n.op; d.src_dtype = n.src_dtype; d.data = n.data; d.offset = n.offset; d.imm = n.imm;
+        if (!n.peers.empty()) { d.n_peers = (int)n.peers.size(); d.peer_block = n.peer_block; d.data = nullptr; for (size_t p = 0; p < n.peers.size(); ++p) d.peer[p] = n.peers[p]; }
         for (auto& [a, s] : n.stride) d.stride[pos(a)] = s;
         if (n.kind == MDIM_NODE_GATHER) { d.n_comp = (int)n.kids.size(); for (size_t c = 0; c < n.kids.size(); ++c) { d.gstride[c] = n.gstride[c]; d.bound[c] = n.bound[c]; } }
         if (n.kind == MDIM_NODE_CONCAT) { d.axis_a[0] = pos(n.pairs[0].a); d.axis_c[0] = n.pairs[0].c; }
         if (n.kind == MDIM_NODE_DIAG) {
             d.n_comp = (int)n.pairs.size();
-            for (size_t p = 0; p < n.pairs.size(); ++p) { d.axis_a[p] = pos(n.pairs[p].a); if (n.pairs[p].b) d.axis_b[p] = pos(n.pairs[p].b); else { d.axis_b[p] = -1; d.axis_c[p] = n.pairs[p].c; } }
+            for (size_t p = 0; p < n.pairs.size(); ++p) {
+                d.axis_a[p] = pos(n.pairs[p].a);
+                if (n.pairs[p].b) { d.axis_b[p] = pos(n.pairs[p].b); d.axis_c[p] = (uint64_t)n.pairs[p].off; }
+                else { d.axis_b[p] = -1; d.axis_c[p] = n.pairs[p].c; }
+            }
         }
     }
     mdim_expr e; std::memset(&e, 0, sizeof e);
@@ -254,6 +339,7 @@ inline void emit_and_run(const NodeP& root, const std::vector<AxisP>& axes, cons
 // ---- View<I, T> (src/view.rs:116-653) ------------------------------------------------------------------------
 template <class I, class T> class View;
 template <class I, class T> class Array;
+template <class I, class T, class U> struct PairView;
 template <class V, class I_, class J_> class Rows;
 
 namespace detail {
@@ -267,32 +353,31 @@ inline NodeP make_unary(int op, int dtype, const NodeP& a) {
 template <class A, class B, class = void> struct Bc;  // primary: no impl => compile error, like a missing trait impl
 template <class A> struct Bc<A, A, std::enable_if_t<(n_leaves<A> == 1) && !std::is_same_v<A, Unit> && std::is_same_v<typename Ix<A>::Flat, std::tuple<A>>>> {  // NonTuple vs itself
     using R = A;
-    static SizeOf<A> go(const SizeOf<A>& sa, const SizeOf<A>& sb, Groups& ga, Groups& gb, Groups& out, Table& t) {
+    static SizeOf<A> go(const SizeOf<A>& sa, const SizeOf<A>& sb, Groups& ga, Groups& gb, Groups& out, Table& tv, Table& tw) {
         if (!(sa == sb)) throw Panic(MDIM_ERR_SIZE, "Unequal sizes");  // src/broadcast.rs:38
         auto a = ga.front(), b = gb.front(); ga.erase(ga.begin()); gb.erase(gb.begin());
-        for (size_t k = 0; k < a.size(); ++k) t.push_back({b[k].get(), rename_to(a[k])});
-        out.push_back(a); return sa;
+        out.push_back(unify_group(a, b, tv, tw)); return sa;  // the two sides may split this axis differently (to_usize)
     }
 };
 template <class B> struct Bc<Unit, B, std::enable_if_t<!std::is_same_v<B, Unit>>> {  // () expands to any Expand type
     using R = B;
-    static SizeOf<B> go(const Unit&, const SizeOf<B>& sb, Groups&, Groups& gb, Groups& out, Table&) {
+    static SizeOf<B> go(const Unit&, const SizeOf<B>& sb, Groups&, Groups& gb, Groups& out, Table&, Table&) {
         for (size_t k = 0; k < n_leaves<B>; ++k) { out.push_back(gb.front()); gb.erase(gb.begin()); } return sb;
     }
 };
 template <class A> struct Bc<A, Unit, std::enable_if_t<!std::is_same_v<A, Unit>>> {
     using R = A;
-    static SizeOf<A> go(const SizeOf<A>& sa, const Unit&, Groups& ga, Groups&, Groups& out, Table&) {
+    static SizeOf<A> go(const SizeOf<A>& sa, const Unit&, Groups& ga, Groups&, Groups& out, Table&, Table&) {
         for (size_t k = 0; k < n_leaves<A>; ++k) { out.push_back(ga.front()); ga.erase(ga.begin()); } return sa;
     }
 };
 template <class... As, class... Bs> struct Bc<std::tuple<As...>, std::tuple<Bs...>, std::enable_if_t<(sizeof...(As) == sizeof...(Bs)) && (sizeof...(As) > 0)>> {
     using R = std::tuple<typename Bc<As, Bs>::R...>;
-    static SizeOf<R> go(const std::tuple<SizeOf<As>...>& sa, const std::tuple<SizeOf<Bs>...>& sb, Groups& ga, Groups& gb, Groups& out, Table& t) {
-        return go_(sa, sb, ga, gb, out, t, std::index_sequence_for<As...>{});
+    static SizeOf<R> go(const std::tuple<SizeOf<As>...>& sa, const std::tuple<SizeOf<Bs>...>& sb, Groups& ga, Groups& gb, Groups& out, Table& tv, Table& tw) {
+        return go_(sa, sb, ga, gb, out, tv, tw, std::index_sequence_for<As...>{});
     }
-    template <size_t... K> static SizeOf<R> go_(const std::tuple<SizeOf<As>...>& sa, const std::tuple<SizeOf<Bs>...>& sb, Groups& ga, Groups& gb, Groups& out, Table& t, std::index_sequence<K...>) {
-        return SizeOf<R>{Bc<As, Bs>::go(std::get<K>(sa), std::get<K>(sb), ga, gb, out, t)...};
+    template <size_t... K> static SizeOf<R> go_(const std::tuple<SizeOf<As>...>& sa, const std::tuple<SizeOf<Bs>...>& sb, Groups& ga, Groups& gb, Groups& out, Table& tv, Table& tw, std::index_sequence<K...>) {
+        return SizeOf<R>{Bc<As, Bs>::go(std::get<K>(sa), std::get<K>(sb), ga, gb, out, tv, tw)...};
     }
 };
 }  // namespace detail
@@ -324,9 +409,43 @@ template <class I, class T> class View {
     template <class B, class J> View<typename detail::Bc<I, J>::R, T> binary(const View<J, T>& other) const {
         using R = typename detail::Bc<I, J>::R;
         View<J, T> w = other.fresh();
-        Groups ga = groups_, gb = w.groups(), out; Table t;
-        SizeOf<R> s = detail::Bc<I, J>::go(size_, w.size(), ga, gb, out, t);
-        return View<R, T>(s, out, detail::make_binary(B::code, value_, substitute(w.value(), t)));
+        Groups ga = groups_, gb = w.groups(), out; Table tv, tw;
+        SizeOf<R> s = detail::Bc<I, J>::go(size_, w.size(), ga, gb, out, tv, tw);
+        return View<R, T>(s, out, detail::make_binary(B::code, substitute(value_, tv), substitute(w.value(), tw)));
+    }
+    // zip (src/view.rs:490-497) with ops::Pair (src/ops.rs:25-29): tuple-typed elements are kept as a structure of arrays
+    template <class J, class U> PairView<typename detail::Bc<I, J>::R, T, U> zip(const View<J, U>& other) const {
+        using R = typename detail::Bc<I, J>::R;
+        View<J, U> w = other.fresh();
+        Groups ga = groups_, gb = w.groups(), out; Table tv, tw;
+        SizeOf<R> s = detail::Bc<I, J>::go(size_, w.size(), ga, gb, out, tv, tw);
+        return PairView<R, T, U>{View<R, T>(s, out, substitute(value_, tv)), View<R, U>(s, out, substitute(w.value(), tw))};
+    }
+    // enumerate (src/view.rs:267-269) for a usize-indexed view: (index, value)
+    PairView<I, usize, T> enumerate() const {
+        static_assert(std::is_same_v<I, usize>, "enumerate: this header lowers usize-indexed views (compound indices: the Python mirror)");
+        auto n = std::make_shared<Node>(); n->kind = MDIM_NODE_IOTA; n->dtype = MDIM_U64;
+        int64_t acc = 1;
+        for (auto it = groups_[0].rbegin(); it != groups_[0].rend(); ++it) { n->stride.push_back({*it, acc}); acc *= (int64_t)(*it)->length; }
+        return PairView<I, usize, T>{View<I, usize>(size_, groups_, n), *this};
+    }
+    // The block of this view owned by `rank` when its OUTERMOST position axis is cut into `world` contiguous blocks (the north
+    // star's partitioning; multidimension_b200/sharding.py::shard_view): the outer coordinate becomes lo + k.
+    View shard(int rank, int world) const {
+        static_assert(n_leaves<I> >= 1, "a rank-0 view has no axis to shard");
+        if (groups_.empty() || groups_[0].size() != 1) throw Unsupported("the outermost axis has been re-split: shard before merging it");
+        const AxisP outer = groups_[0][0];
+        const uint64_t q = outer->length / (uint64_t)world, r = outer->length % (uint64_t)world;
+        const uint64_t lo = (uint64_t)rank * q + std::min<uint64_t>((uint64_t)rank, r), n = q + ((uint64_t)rank < r ? 1 : 0);
+        auto k = std::make_shared<Axis>(Axis{n});
+        Sub_ sub; sub.constant = (int64_t)lo; sub.terms.push_back({k, 1});
+        Table t{{outer.get(), sub}};
+        Groups g = groups_; g[0] = {k};
+        std::vector<uint64_t> flat_sz; Ix<I>::flat_size(size_, flat_sz);
+        if (flat_sz.empty()) throw Unsupported("the outermost axis must be a usize axis to be sharded");
+        flat_sz[0] = n; flat_sz.push_back(0);
+        const uint64_t* it = flat_sz.data();
+        return View(Ix<I>::build(it), g, substitute(value_, t));
     }
     template <class J> auto operator+(const View<J, T>& o) const { return binary<Add>(o); }
     template <class J> auto operator-(const View<J, T>& o) const { return binary<Sub>(o); }
@@ -349,7 +468,7 @@ template <class I, class T> class View {
     View<std::tuple<I, I>, T> diagonal(T zero) const {
         Groups twin; auto n = std::make_shared<Node>();
         n->kind = MDIM_NODE_DIAG; n->dtype = DType<T>::v; n->kids = {value_}; n->imm = scalar_of(zero);
-        for (auto& grp : groups_) { twin.emplace_back(); for (auto& a : grp) { auto b = std::make_shared<Axis>(*a); twin.back().push_back(b); n->pairs.push_back({a, b, 0}); } }
+        for (auto& grp : groups_) { twin.emplace_back(); for (auto& a : grp) { auto b = std::make_shared<Axis>(*a); twin.back().push_back(b); n->pairs.push_back({a, b, 0, 0}); } }
         Groups g = groups_; g.insert(g.end(), twin.begin(), twin.end());
         return View<std::tuple<I, I>, T>(std::make_tuple(size_, size_), g, n->pairs.empty() ? value_ : NodeP(n));
     }
@@ -400,16 +519,14 @@ template <class I, class T> class View {
         const uint64_t nv = std::get<1>(sv), nw = std::get<1>(sw);
         auto K = std::make_shared<Axis>(Axis{nv + nw});
         Table tv{{groups_[ni][0].get(), rename_to(K)}}, tw;
-        for (size_t g = 0; g < groups_.size(); ++g) {
-            if (g == ni) continue;
-            if (groups_[g].size() != w.groups()[g].size()) throw Unsupported("concat of views whose axes are grouped differently");
-            for (size_t k = 0; k < groups_[g].size(); ++k) tw.push_back({w.groups()[g][k].get(), rename_to(groups_[g][k])});
-        }
+        Groups g = groups_;
+        for (size_t k = 0; k < groups_.size(); ++k)
+            if (k != ni) g[k] = unify_group(groups_[k], w.groups()[k], tv, tw);  // the two sides may split an axis differently (to_usize)
         Sub_ shifted; shifted.constant = -(int64_t)nv; shifted.terms.push_back({K, 1});
         tw.push_back({w.groups()[ni][0].get(), shifted});
         auto n = std::make_shared<Node>();
-        n->kind = MDIM_NODE_CONCAT; n->dtype = DType<T>::v; n->kids = {substitute(value_, tv), substitute(w.value(), tw)}; n->pairs.push_back({K, nullptr, nv});
-        Groups g = groups_; g[ni] = {K};
+        n->kind = MDIM_NODE_CONCAT; n->dtype = DType<T>::v; n->kids = {substitute(value_, tv), substitute(w.value(), tw)}; n->pairs.push_back({K, nullptr, nv, 0});
+        g[ni] = {K};
         return View<Mid, T>(SizeOf<Mid>{std::get<0>(sv), nv + nw, std::get<2>(sv)}, g, NodeP(n));
     }
     // from_usize::<I, X, J>(size of X) (src/view.rs:352-363, 993-1021): the usize axis is re-indexed by X;
@@ -422,11 +539,17 @@ template <class I, class T> class View {
         if (length<X>(xsize) != std::get<1>(s))  // assert_eq!(X::length(size), old_size), src/view.rs:361
             throw Panic(MDIM_ERR_SIZE, "assertion `left == right` failed\n  left: " + std::to_string(length<X>(xsize)) + "\n right: " + std::to_string(std::get<1>(s)));
         const size_t ni = n_leaves<I0>;
-        if (groups_[ni].size() != 1) throw Unsupported("from_usize of an axis that is a merged group (to_usize) needs device div/mod");
-        Groups gx = fresh_groups<X>(xsize);
-        Sub_ sub; int64_t acc = 1; auto fx = flat(gx);
-        for (auto it = fx.rbegin(); it != fx.rend(); ++it) { sub.terms.push_back({*it, acc}); acc *= (int64_t)(*it)->length; }
-        Table t{{groups_[ni][0].get(), sub}};
+        // the usize axis may itself be a merged group (a to_usize further down): both factorisations are rewritten over their refinement
+        std::vector<uint64_t> lold, lx, pieces; std::vector<std::vector<size_t>> mo, mx;
+        for (auto& a : groups_[ni]) lold.push_back(a->length);
+        Ix<X>::lengths(xsize, lx);
+        refine(lold, lx, pieces, mo, mx);
+        std::vector<AxisP> axes;
+        for (uint64_t n : pieces) axes.push_back(std::make_shared<Axis>(Axis{n}));
+        Table t;
+        for (size_t k = 0; k < groups_[ni].size(); ++k) { std::vector<AxisP> pc; for (size_t q : mo[k]) pc.push_back(axes[q]); t.push_back({groups_[ni][k].get(), sub_of(pc)}); }
+        Groups gx;
+        for (size_t k = 0; k < lx.size(); ++k) { gx.emplace_back(); for (size_t q : mx[k]) gx.back().push_back(axes[q]); }
         Groups g(groups_.begin(), groups_.begin() + ni);
         g.insert(g.end(), gx.begin(), gx.end());
         g.insert(g.end(), groups_.begin() + ni + 1, groups_.end());
@@ -574,11 +697,118 @@ template <class I, class T> Array<I, T> View<I, T>::collect(const Executor& ex) 
     return Array<I, T>(typename Array<I, T>::Shared{}, size_, out);
 }
 
+// ---- tuple-typed elements (zip without an operator, enumerate): a structure of arrays, one View per scalar leaf -------------
+template <class I, class T, class U> struct PairView {
+    View<I, T> first; View<I, U> second;
+    const SizeOf<I>& size() const { return first.size(); }
+    // zip(..).map(|(x, y)| x (B) y): the pair consumed by an operator (what `a.zip(b).map(closure)` lowers to)
+    template <class B> View<I, T> binary() const { static_assert(std::is_same_v<T, U>, "operands of different element types"); return View<I, T>(first.size(), first.groups(), detail::make_binary(B::code, first.value(), second.value())); }
+    std::pair<Array<I, T>, Array<I, U>> collect(const Executor& ex) const { return {first.collect(ex), second.collect(ex)}; }
+};
+
+// ---- device-resident Arrays: the boxed buffer in HBM, optionally sharded over the GPUs of the box ------------------------------------
+// The C ABI entry points, looked up in an already loaded libmdim_b200.so (this header links nothing).
+struct Api {
+    int (*init)(int, mdim_ctx**) = nullptr; int (*shutdown)(mdim_ctx*) = nullptr; int (*sync)(mdim_ctx*) = nullptr;
+    int (*last_error)(mdim_ctx*, mdim_error_info*) = nullptr;
+    int (*buf_alloc)(mdim_ctx*, size_t, void**) = nullptr; int (*buf_free)(mdim_ctx*, void*) = nullptr;
+    int (*upload)(mdim_ctx*, void*, const void*, size_t) = nullptr; int (*download)(mdim_ctx*, void*, const void*, size_t) = nullptr;
+    int (*collect)(mdim_ctx*, const mdim_expr*, void*, uint32_t) = nullptr; int (*collect_host)(mdim_ctx*, const mdim_expr*, void*, uint32_t) = nullptr;
+    int (*comm_unique_id)(uint8_t*) = nullptr; int (*comm_init)(mdim_ctx*, int, int, const uint8_t*) = nullptr; int (*comm_destroy)(mdim_ctx*) = nullptr;
+    int (*allgather)(mdim_ctx*, const void*, void*, size_t) = nullptr; int (*allreduce)(mdim_ctx*, void*, size_t, int, int) = nullptr; int (*barrier)(mdim_ctx*) = nullptr;
+    int (*peer_table)(mdim_ctx*, void*, size_t, void**) = nullptr; int (*peer_table_close)(mdim_ctx*) = nullptr;
+    template <class Sym> static Api load(Sym&& sym) {  // sym(name) -> void*
+        Api a;
+#define MDIM_API(field, name) a.field = reinterpret_cast<decltype(a.field)>(sym(name))
+        MDIM_API(init, "mdim_init"); MDIM_API(shutdown, "mdim_shutdown"); MDIM_API(sync, "mdim_sync"); MDIM_API(last_error, "mdim_last_error");
+        MDIM_API(buf_alloc, "mdim_buf_alloc"); MDIM_API(buf_free, "mdim_buf_free"); MDIM_API(upload, "mdim_upload"); MDIM_API(download, "mdim_download");
+        MDIM_API(collect, "mdim_collect"); MDIM_API(collect_host, "mdim_collect_host");
+        MDIM_API(comm_unique_id, "mdim_comm_unique_id"); MDIM_API(comm_init, "mdim_comm_init"); MDIM_API(comm_destroy, "mdim_comm_destroy");
+        MDIM_API(allgather, "mdim_allgather"); MDIM_API(allreduce, "mdim_allreduce"); MDIM_API(barrier, "mdim_barrier");
+        MDIM_API(peer_table, "mdim_peer_table"); MDIM_API(peer_table_close, "mdim_peer_table_close");
+#undef MDIM_API
+        return a;
+    }
+    void check(mdim_ctx* ctx, int st) const {
+        if (st == MDIM_OK) return;
+        mdim_error_info info; std::memset(&info, 0, sizeof info);
+        last_error(ctx, &info);
+        if (info.status == st && info.message[0]) throw Panic(st, info);
+        throw Panic(st, "mdim status " + std::to_string(st));
+    }
+    // device-resident operands and result: mdim_collect
+    Executor device_resident(mdim_ctx* ctx) const {
+        const Api self = *this;
+        return Executor{[self, ctx](const mdim_expr* e, void* out, mdim_error_info* err) {
+            const int st = self.collect(ctx, e, out, 0);
+            if (st != MDIM_OK && err) self.last_error(ctx, err);
+            return st;
+        }};
+    }
+};
+
+template <class I, class T> class DeviceArray : public View<I, T> {
+  public:
+    using Store = std::conditional_t<std::is_same_v<T, bool>, uint8_t, T>;
+    // Array::new + upload (src/array.rs:28-30)
+    DeviceArray(const Api& api, mdim_ctx* ctx, const SizeOf<I>& size, const std::vector<Store>& items) : View<I, T>(size, fresh_groups<I>(size), nullptr), buf_(alloc(api, ctx, items.size())) {
+        if (items.size() != length<I>(size)) throw Panic(MDIM_ERR_SIZE, "assertion `left == right` failed");  // src/array.rs:12
+        api.check(ctx, api.upload(ctx, buf_->ptr, items.data(), items.size() * sizeof(Store)));
+        leaf({}, 0);
+    }
+    // an uninitialised result buffer (collect target)
+    DeviceArray(const Api& api, mdim_ctx* ctx, const SizeOf<I>& size) : View<I, T>(size, fresh_groups<I>(size), nullptr), buf_(alloc(api, ctx, length<I>(size))) { leaf({}, 0); }
+    // An Array sharded over the GPUs of the box in equal blocks of `block` elements, block p at peers[p] (mdim_peer_table):
+    // every kernel reads the owning GPU's HBM over NVLink; a transpose does its all-to-all inside the tile loads.
+    static DeviceArray sharded(const SizeOf<I>& size, const std::vector<const void*>& peers, uint64_t block, std::shared_ptr<void> keep = nullptr) {
+        DeviceArray a(size, std::move(keep));
+        a.leaf(peers, block);
+        return a;
+    }
+    void* device_ptr() const { return buf_ ? buf_->ptr : nullptr; }
+    size_t nbytes() const { return (size_t)this->len() * sizeof(Store); }
+    std::vector<Store> to_raw() const {  // src/array.rs:54: downloads
+        std::vector<Store> out(this->len());
+        buf_->api.check(buf_->ctx, buf_->api.download(buf_->ctx, out.data(), buf_->ptr, out.size() * sizeof(Store)));
+        return out;
+    }
+  private:
+    struct Buf { Api api; mdim_ctx* ctx; void* ptr; ~Buf() { if (ptr) api.buf_free(ctx, ptr); } };
+    static std::shared_ptr<Buf> alloc(const Api& api, mdim_ctx* ctx, size_t n) {
+        void* p = nullptr;
+        api.check(ctx, api.buf_alloc(ctx, n * sizeof(Store), &p));
+        return std::shared_ptr<Buf>(new Buf{api, ctx, p});
+    }
+    DeviceArray(const SizeOf<I>& size, std::shared_ptr<void> keep) : View<I, T>(size, fresh_groups<I>(size), nullptr), keep_(std::move(keep)) {}
+    void leaf(const std::vector<const void*>& peers, uint64_t block) {
+        auto n = std::make_shared<Node>();
+        n->kind = MDIM_NODE_LEAF; n->dtype = DType<T>::v; n->data = buf_ ? buf_->ptr : nullptr; n->keep = buf_ ? std::shared_ptr<void>(buf_, buf_.get()) : keep_;
+        n->peers = peers; n->peer_block = block;
+        auto ax = flat(this->groups()); int64_t acc = 1;
+        for (size_t k = ax.size(); k-- > 0;) { n->stride.push_back({ax[k], acc}); acc *= (int64_t)ax[k]->length; }
+        this->value_ = n;
+    }
+    std::shared_ptr<Buf> buf_;
+    std::shared_ptr<void> keep_;
+};
+// View::collect into HBM: ONE fused kernel, operands and result device-resident
+template <class I, class T> DeviceArray<I, T> collect_device(const View<I, T>& v, const Api& api, mdim_ctx* ctx) {
+    DeviceArray<I, T> out(api, ctx, v.size());
+    emit_and_run(v.value(), flat(v.groups()), api.device_resident(ctx), out.device_ptr());
+    return out;
+}
+
 // ---- All<I> (src/index.rs:177-186) for usize, and Scalar<T> (src/view.rs:1399-1408) ------------------------------
 inline View<usize, usize> all(uint64_t size) {
     Groups g = fresh_groups<usize>(size);
     auto n = std::make_shared<Node>(); n->kind = MDIM_NODE_IOTA; n->dtype = MDIM_U64; n->stride.push_back({g[0][0], 1});
     return View<usize, usize>(size, g, n);
+}
+// All<Reversed>: position p holds Reversed(size - 1 - p) (src/int.rs:82-84); the element is its usize payload
+inline View<Reversed, usize> all_reversed(uint64_t size) {
+    Groups g = fresh_groups<Reversed>(size);
+    auto n = std::make_shared<Node>(); n->kind = MDIM_NODE_IOTA; n->dtype = MDIM_U64; n->offset = (int64_t)size - 1; n->stride.push_back({g[0][0], -1});
+    return View<Reversed, usize>(size, g, n);
 }
 template <class T> View<Unit, T> Scalar(T value) {
     auto n = std::make_shared<Node>(); n->kind = MDIM_NODE_CONST; n->dtype = DType<T>::v; n->imm = scalar_of(value);

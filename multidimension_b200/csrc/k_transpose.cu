@@ -488,15 +488,17 @@ static bool launch_transpose_tma(const TransposePlan& T, void* out, cudaStream_t
     CUtensorMap dm;
     if (!tma_encode(&dm, out, es, T.len_b, T.len_a, T.out_stride_a, T.n_batch, T.batch_len, T.batch_out_stride)) return false;
     if (T.n_peers > 1) {
-        // row-sharded 2-D source, peer p holding rows [p * rows_pp, (p + 1) * rows_pp): one tensor map per peer, and a tile
-        // never straddles two of them
-        if (T.n_batch != 0 || T.src_offset != 0 || T.src_stride_b != (int64_t)T.len_a || T.len_a == 0 || T.peer_block % (T.len_a * 64) != 0) return false;
-        const uint64_t rows_pp = T.peer_block / T.len_a;
+        // row-sharded 2-D source of row pitch S, peer p holding rows [p * rows_pp, (p + 1) * rows_pp); this launch reads the column
+        // window [src_offset, src_offset + len_a) of every row (a rank's block of the transposed rows).  One tensor map per peer,
+        // and a tile never straddles two of them.
+        const int64_t S = T.src_stride_b;
+        if (T.n_batch != 0 || S <= 0 || T.src_offset < 0 || T.src_offset + (int64_t)T.len_a > S || T.peer_block % ((uint64_t)S * 64) != 0) return false;
+        const uint64_t rows_pp = T.peer_block / (uint64_t)S;
         if (rows_pp * (uint64_t)T.n_peers != T.len_b) return false;
         TmaSrcMaps<MDIM_MAX_PEERS> sm;
         memset(&sm, 0, sizeof sm);
         for (int p = 0; p < T.n_peers; ++p)
-            if (!tma_encode(&sm.m[p], T.peer[p], es, T.len_a, rows_pp, T.src_stride_b, 0, nullptr, nullptr)) return false;
+            if (!tma_encode(&sm.m[p], (const char*)T.peer[p] + T.src_offset * es, es, T.len_a, rows_pp, S, 0, nullptr, nullptr)) return false;
         A.n_peers = T.n_peers; A.tiles_b_per_peer = (uint32_t)(rows_pp / 64);
         return es == 4 ? launch_tma1<4, MDIM_MAX_PEERS>(sm, dm, A, stream) : launch_tma1<8, MDIM_MAX_PEERS>(sm, dm, A, stream);
     }

@@ -212,6 +212,81 @@ int main(int argc, char** argv) {
             }
         CHECK(same);
     }
+    // ---- round 2: the remaining leaf index kinds, re-split axes, tuple-typed elements, shards ----------
+    {   // Reversed (src/int.rs:58-86): position p <-> index size-1-p; row / at count backwards
+        using RU = std::tuple<Reversed, usize>;
+        Array<RU, usize> a(std::make_tuple(uint64_t(3), uint64_t(2)), {0, 1, 10, 11, 20, 21});
+        CHECK(eq(a.row<Reversed, usize>(Reversed{0}).collect(ex).as_ref(), {20ull, 21ull}));
+        CHECK(a.at(RU{Reversed{2}, 1}) == 1);
+        CHECK(eq(all_reversed(4).collect(ex).as_ref(), {3ull, 2ull, 1ull, 0ull}));   // src/int.rs:82-84
+        try { a.row<Reversed, usize>(Reversed{3}); CHECK(false); } catch (const Panic& p) { CHECK(p.status == MDIM_ERR_OOB); }
+    }
+    {   // Option<I> (src/index.rs:244-276): None is position 0, Some(i) is 1 + i.to_usize()
+        using OU = std::tuple<Option<usize>, usize>;
+        Array<OU, usize> a(std::make_tuple(uint64_t(2), uint64_t(2)), {0, 1, 10, 11, 20, 21});
+        CHECK(eq(a.row<Option<usize>, usize>(None<usize>()).collect(ex).as_ref(), {0ull, 1ull}));
+        CHECK(eq(a.row<Option<usize>, usize>(Some<usize>(1)).collect(ex).as_ref(), {20ull, 21ull}));
+        CHECK(a.len() == 6);
+    }
+    {   // Fixed<N> is range-checked where the reference's slice access would panic (src/array.rs:86)
+        Array<std::tuple<Fixed<3>, usize>, usize> a(std::make_tuple(Unit{}, uint64_t(2)), {0, 1, 10, 11, 20, 21});
+        CHECK(eq(a.row<Fixed<3>, usize>(Fixed<3>{2}).collect(ex).as_ref(), {20ull, 21ull}));
+        try { a.row<Fixed<3>, usize>(Fixed<3>{7}); CHECK(false); } catch (const Panic& p) { CHECK(p.status == MDIM_ERR_OOB); }
+    }
+    {   // an axis merged by to_usize zipped with a plain axis of the same length: the two splits are unified
+        Array<U2, usize> a(std::make_tuple(uint64_t(2), uint64_t(3)), {0, 1, 2, 3, 4, 5});
+        Array<usize, usize> b(6, {0, 10, 20, 30, 40, 50});
+        auto af = a.iso<std::tuple<Unit, U2, Unit>>().to_usize<Unit, U2, Unit>().iso<usize>();
+        CHECK(eq((af + b).collect(ex).as_ref(), {0ull, 11ull, 22ull, 33ull, 44ull, 55ull}));
+        CHECK(eq((b + af).collect(ex).as_ref(), {0ull, 11ull, 22ull, 33ull, 44ull, 55ull}));
+        Array<U2, usize> e(std::make_tuple(uint64_t(3), uint64_t(2)), {0, 1, 2, 3, 4, 5});
+        auto ef = e.iso<std::tuple<Unit, U2, Unit>>().to_usize<Unit, U2, Unit>().iso<usize>();
+        try { (af + ef); CHECK(false); } catch (const Unsupported&) { CHECK(true); }   // (2,3) vs (3,2): no common refinement, declined loudly
+        // from_usize of a merged axis: (2,3) -> 6 -> (3,2)
+        auto resplit = a.iso<std::tuple<Unit, U2, Unit>>().to_usize<Unit, U2, Unit>();
+        try { resplit.from_usize<Unit, U2, Unit>(std::make_tuple(uint64_t(3), uint64_t(2))); CHECK(false); } catch (const Unsupported&) { CHECK(true); }
+        CHECK(eq(resplit.from_usize<Unit, U2, Unit>(std::make_tuple(uint64_t(2), uint64_t(3))).collect(ex).as_ref(), a.as_ref()));
+    }
+    {   // zip / enumerate: tuple-typed elements as a structure of arrays (src/view.rs:451-461, 257-266)
+        Array<usize, usize> a(3, {7, 8, 9});
+        Array<usize, float> b(3, {0.5f, 1.5f, 2.5f});
+        auto ab = a.zip(b).collect(ex);
+        CHECK(eq(ab.first.as_ref(), {7ull, 8ull, 9ull}) && eq(ab.second.as_ref(), {0.5f, 1.5f, 2.5f}));
+        auto en = a.enumerate().collect(ex);
+        CHECK(eq(en.first.as_ref(), {0ull, 1ull, 2ull}) && eq(en.second.as_ref(), {7ull, 8ull, 9ull}));
+        Array<usize, usize> c(3, {1, 2, 3});
+        CHECK(eq(a.zip(c).binary<Mul>().collect(ex).as_ref(), {7ull, 16ull, 27ull}));  // zip(..).map(|(x, y)| x * y)
+    }
+    {   // shard(rank, world): the blocks of all ranks tile the unsharded collect, including under a diagonal
+        Array<U2, float> m(std::make_tuple(uint64_t(5), uint64_t(3)), {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14});
+        auto t = m.transpose<Unit, usize, usize, Unit>().iso<U2>();
+        auto full = t.collect(ex).as_ref();
+        std::vector<float> got;
+        for (int r = 0; r < 2; ++r) { auto part = t.shard(r, 2).collect(ex).as_ref(); got.insert(got.end(), part.begin(), part.end()); }
+        CHECK(got == full);
+        auto d = (all(4) + Scalar<usize>(10)).diagonal(0);
+        auto dfull = d.collect(ex).as_ref();
+        std::vector<uint64_t> dgot;
+        for (int r = 0; r < 3; ++r) { auto part = d.shard(r, 3).collect(ex).as_ref(); dgot.insert(dgot.end(), part.begin(), part.end()); }
+        CHECK(dgot == dfull);
+    }
+    if (ctx) {   // device-resident Arrays through mdim_collect, and a "sharded" Array whose peers are blocks of one local buffer
+        const Api api = Api::load([&](const char* name) { return sym(lib, name); });
+        const uint64_t M = 128, N = 192;
+        std::vector<float> mv(M * N); for (size_t i = 0; i < mv.size(); ++i) mv[i] = (float)i * 0.25f;
+        DeviceArray<U2, float> dm(api, ctx, std::make_tuple(M, N), mv);
+        auto tr = collect_device(dm.transpose<Unit, usize, usize, Unit>(), api, ctx).to_raw();
+        bool same = tr.size() == mv.size();
+        for (uint64_t x = 0; x < N && same; ++x) for (uint64_t y = 0; y < M; ++y) same = same && tr[x * M + y] == mv[y * N + x];
+        CHECK(same);
+        std::vector<const void*> peers; const uint64_t block = M * N / 2;
+        for (int p = 0; p < 2; ++p) peers.push_back((const char*)dm.device_ptr() + (size_t)p * block * 4);
+        auto sh = DeviceArray<U2, float>::sharded(std::make_tuple(M, N), peers, block);
+        auto tr2 = collect_device(sh.transpose<Unit, usize, usize, Unit>().iso<U2>().shard(1, 2), api, ctx).to_raw();
+        same = tr2.size() == mv.size() / 2;
+        for (uint64_t x = N / 2; x < N && same; ++x) for (uint64_t y = 0; y < M; ++y) same = same && tr2[(x - N / 2) * M + y] == mv[y * N + x];
+        CHECK(same);
+    }
     std::printf("%s: %d checks, %d failures\n", argv[1], checks, failures);
     if (ctx) ((int (*)(mdim_ctx*))sym(lib, "mdim_shutdown"))(ctx);
     return failures ? 1 : 0;

@@ -59,3 +59,20 @@ def test_c_abi_collectives_and_peer_tables(world, tmp_path):
         assert p["ar_prod"].tolist() == [int(np.prod(ranks + 1)), int(np.prod(10 - ranks)), 7 ** world]
         assert p["ar_min"].tolist() == [1, 10 - (world - 1), 7]
         assert p["ar_max"].tolist() == [world, 10, 7]
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_runs_the_two_gpu_transpose(tmp_path):
+    """The typed C++ host mirror drives two GPUs through the C ABI alone: communicator, peer table, the peer-mapped
+    transpose of a row-sharded Array, all-gather + transpose, partial fold + all-reduce (tests/cpp/test_multi_gpu.cpp)."""
+    world = 2
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import multidimension_b200 as P
+    exe = str(tmp_path / "test_multi_gpu")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-o", exe, os.path.join(HERE, "cpp", "test_multi_gpu.cpp"), "-ldl"], check=True)
+    rdv = str(tmp_path / "rendezvous")
+    procs = [subprocess.Popen([exe, str(r), str(world), P.LIB_PATH, rdv], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "0 failures" in o, f"rank {r}:\n{o[-2000:]}"
