@@ -258,6 +258,15 @@ int mdim_allreduce(mdim_ctx* ctx, void* data_device, size_t n, int dtype, int op
 int mdim_barrier(mdim_ctx* ctx);                                                          /* + waits for the stream */
 int mdim_peer_table(mdim_ctx* ctx, void* local_device, size_t block_bytes, void* peers[MDIM_MAX_PEERS]);
 int mdim_peer_table_close(mdim_ctx* ctx);                                                 /* unmaps every peer block */
+/* Fold over the SHARDED (outermost) axis, BIT-IDENTICAL to the reference's sequential chain (src/view.rs:617-622, 250-252):
+ * `local_rows` = this rank's rows (dense row-major n_rows_local x n_cols, device memory), ranks in index order;
+ * out[c] = (((init (op) x[0][c]) (op) x[1][c]) ... ) over ALL ranks' rows, on EVERY rank.  One fused kernel per GPU: the running
+ * values travel rank to rank through peer-mapped HBM, pipelined over column slices (csrc/k_fold_ring.cu) — no all-reduce, no
+ * reassociation.  op: MDIM_ADD, SUB, MUL, AND, OR, XOR; 4- and 8-byte dtypes; n_cols <= 2^20 per call, rows 16-byte aligned.
+ * Asynchronous on the context's stream; mdim_fold_sharded_axis_status reports (and clears) a peer that never arrived. */
+int mdim_fold_sharded_axis(mdim_ctx* ctx, const void* local_rows, uint64_t n_rows_local, uint64_t n_cols, int dtype, int op, mdim_scalar init,
+                           void* out_device);
+int mdim_fold_sharded_axis_status(mdim_ctx* ctx);
 
 /* Run-time specialisation (NVRTC) of `e`'s op tree, compile step only: needs no GPU.  0 = compiles for
  * sm_100a; MDIM_ERR_UNSUPPORTED = NVRTC not installed or the plan has a pre-built kernel; `log` gets details. */

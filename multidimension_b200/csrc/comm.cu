@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "ctx.hpp"
+#include "kernels.cuh"
 
 namespace mdim {
 
@@ -84,13 +85,23 @@ struct Comm {
     size_t scratch_bytes = 0;
     struct Opened { cudaIpcMemHandle_t handle; void* base; };  // one mapping per peer ALLOCATION, however many blocks live in it
     std::vector<Opened> opened;  // IPC mappings made by mdim_peer_table, closed by mdim_peer_table_close / shutdown
+    // state of the pipelined fold over the sharded axis (k_fold_ring.cu): one allocation per rank, mapped into every rank
+    //   [inbox: kRingCap x 8 B][result: kRingCap x 8 B][flag_in: kRingSlices x 4 B][flag_final: kRingSlices x 4 B][error: 4 B]
+    char* ring = nullptr;
+    void* ring_peer[MDIM_MAX_PEERS] = {nullptr};
+    uint32_t ring_epoch = 0;
 };
+constexpr uint64_t kRingCap = 1ull << 20;          // columns per launch (a wider result is folded in several launches)
+constexpr uint64_t kRingSlices = kRingCap / 256;   // 256 columns per slice (k_fold_ring.cu)
+constexpr size_t kRingInboxOff = 0, kRingResultOff = kRingCap * 8, kRingFlagInOff = 2 * kRingCap * 8, kRingFlagFinalOff = kRingFlagInOff + kRingSlices * 4,
+                 kRingErrorOff = kRingFlagFinalOff + kRingSlices * 4, kRingBytes = kRingErrorOff + 256;
 
 void comm_destroy(mdim_ctx* ctx) {
     Comm* c = ctx->comm;
     if (!c) return;
     for (const Comm::Opened& o : c->opened) cudaIpcCloseMemHandle(o.base);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->ring) cudaFree(c->ring);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     delete c;
     ctx->comm = nullptr;
@@ -264,6 +275,75 @@ int mdim_peer_table(mdim_ctx* ctx, void* local_device, size_t block_bytes, void*
             c->opened.push_back({all[(size_t)p].handle, mapped});
         }
         peers[p] = (char*)mapped + all[(size_t)p].offset;
+    }
+    return MDIM_OK;
+}
+
+// Collective.  `local_rows` = this rank's rows of an Array whose OUTERMOST axis is sharded over the ranks in rank order
+// (dense row-major, n_rows_local x n_cols, device memory); `out` (n_cols elements, device memory, on EVERY rank) receives
+//   out[c] = (((init (op) x[0][c]) (op) x[1][c]) ... (op) x[I-1][c])   over ALL ranks' rows in index order
+// — the reference's sequential fold (src/view.rs:617-622, 250-252) bit for bit, unlike partial folds + all-reduce.  One fused
+// kernel per GPU: the running values travel from rank to rank through peer-mapped HBM, pipelined over column slices
+// (csrc/k_fold_ring.cu).  op: ADD, SUB, MUL, AND, OR, XOR; 4- and 8-byte dtypes.  Asynchronous on the context's stream.
+int mdim_fold_sharded_axis(mdim_ctx* ctx, const void* local_rows, uint64_t n_rows_local, uint64_t n_cols, int dtype, int op, mdim_scalar init, void* out_device) {
+    if (!ctx || !ctx->comm) return ctx ? set_error(ctx, MDIM_ERR_INVALID, "no communicator: call mdim_comm_init") : MDIM_ERR_INVALID;
+    if (!local_rows || !out_device) return MDIM_ERR_INVALID;
+    const int es = dtype_size(dtype);
+    if (es != 4 && es != 8) return set_error(ctx, MDIM_ERR_UNSUPPORTED, "fold over the sharded axis: 4- and 8-byte element types");
+    if (!(op == MDIM_ADD || op == MDIM_SUB || op == MDIM_MUL || op == MDIM_AND || op == MDIM_OR || op == MDIM_XOR))
+        return set_error(ctx, MDIM_ERR_UNSUPPORTED, "fold over the sharded axis: ADD, SUB, MUL, AND, OR, XOR");
+    if ((dtype == MDIM_F32 || dtype == MDIM_F64) && op >= MDIM_AND) return set_error(ctx, MDIM_ERR_INVALID, "bitwise fold of floats");
+    if (n_cols == 0 || n_rows_local == 0) return set_error(ctx, MDIM_ERR_UNSUPPORTED, "fold over the sharded axis: every rank must hold at least one row");
+    Comm* c = ctx->comm;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!c->ring) {  // first use: allocate the ring state, zero the flags, map everyone's into everyone (collective)
+        CU(ctx, cudaMalloc(&c->ring, kRingBytes));
+        CU(ctx, cudaMemsetAsync(c->ring, 0, kRingBytes, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        int st = mdim_peer_table(ctx, c->ring, kRingBytes, c->ring_peer);
+        if (st) return st;
+        st = mdim_barrier(ctx);
+        if (st) return st;
+    }
+    const int next = (c->rank + 1) % c->world;
+    for (uint64_t c0 = 0; c0 < n_cols; c0 += kRingCap) {
+        FoldRingArgs A;
+        memset(&A, 0, sizeof A);
+        A.n_rows = n_rows_local; A.n_cols = std::min<uint64_t>(kRingCap, n_cols - c0);
+        A.dtype = dtype; A.op = op; A.esize = es; A.rank = c->rank; A.world = c->world;
+        A.epoch = ++c->ring_epoch;
+        A.init = 0; memcpy(&A.init, &init, (size_t)es);
+        A.inbox = c->ring + kRingInboxOff;
+        A.next_inbox = (char*)c->ring_peer[next] + kRingInboxOff;
+        A.flag_in = (const uint32_t*)(c->ring + kRingFlagInOff);
+        A.next_flag_in = (uint32_t*)((char*)c->ring_peer[next] + kRingFlagInOff);
+        for (int p = 0; p < c->world; ++p) {
+            A.result[p] = (char*)c->ring_peer[p] + kRingResultOff;
+            A.flag_final[p] = (uint32_t*)((char*)c->ring_peer[p] + kRingFlagFinalOff);
+        }
+        A.out = (char*)out_device + c0 * (uint64_t)es;
+        A.error = (uint32_t*)(c->ring + kRingErrorOff);
+        if (n_cols > kRingCap) return set_error(ctx, MDIM_ERR_UNSUPPORTED, "fold over the sharded axis: more than 2^20 columns per call (strided column windows: fold the result in blocks)");
+        const int rc = launch_fold_ring(A, local_rows, ctx->sm_count, ctx->stream);
+        if (rc == -1) return set_error(ctx, MDIM_ERR_UNSUPPORTED, "fold over the sharded axis: the rows must be 16-byte aligned with a 16-byte multiple row length");
+        if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_fold_ring");
+        ctx->launches++;
+        snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "k_fold_ring");
+    }
+    poison_inflight(ctx);
+    return MDIM_OK;
+}
+
+// 1 if a fold over the sharded axis gave up waiting for a peer since the last call (then the outputs are garbage)
+int mdim_fold_sharded_axis_status(mdim_ctx* ctx) {
+    if (!ctx || !ctx->comm || !ctx->comm->ring) return MDIM_OK;
+    uint32_t err = 0;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(&err, ctx->comm->ring + kRingErrorOff, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (err) {
+        CU(ctx, cudaMemsetAsync(ctx->comm->ring + kRingErrorOff, 0, 4, ctx->stream));
+        return set_error(ctx, MDIM_ERR_NCCL, "fold over the sharded axis: a peer did not arrive within the time limit");
     }
     return MDIM_OK;
 }

@@ -54,4 +54,9 @@ const char* launch_transpose(const TransposePlan& T, void* out, int grid, cudaSt
 constexpr int kFoldThreads = 256;
 const char* launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cudaStream_t stream);  // -> name of the kernel launched
 
+// ------------------------------------------------------------------------------------------------
+// Fold over the SHARDED axis, bit-exact, pipelined through the ranks over NVLink (k_fold_ring.cu)
+// ------------------------------------------------------------------------------------------------
+int launch_fold_ring(const FoldRingArgs& A, const void* rows, int sm_count, cudaStream_t stream);
+
 }  // namespace mdim

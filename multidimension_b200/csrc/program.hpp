@@ -177,6 +177,22 @@ struct MemRange { uint64_t lo, hi; };  // [lo, hi) bytes
 // (e.g. a slice of someone else's tensor), so every store must be scalar and the vector-store fast paths are off.
 constexpr uint32_t kPlanScalarOut = 0x10000u;
 
+// k_fold_ring.cu: the bit-exact fold over the sharded axis (one fused compute + exchange kernel per GPU)
+struct FoldRingArgs {
+    uint64_t n_rows, n_cols;   // this rank's rows x the (unsharded) columns
+    int32_t dtype, op, esize, rank, world;
+    uint32_t epoch;            // launch counter of the communicator: flags carry it, so they never need resetting
+    uint64_t init;             // bits of the fold's initial value (rank 0 starts from it)
+    const void* inbox;         // this GPU's inbox: running values written by rank - 1
+    void* next_inbox;          // rank + 1's inbox (peer-mapped)
+    const uint32_t* flag_in;   // per slice, set by rank - 1 after its stores
+    uint32_t* next_flag_in;
+    void* result[MDIM_MAX_PEERS];        // every rank's result area (the last rank writes the finished slices into all of them)
+    uint32_t* flag_final[MDIM_MAX_PEERS];
+    void* out;
+    uint32_t* error;           // set to 1 when a peer did not arrive in time
+};
+
 struct Plan {
     int32_t kind;
     uint32_t flags;      // the MDIM_COLLECT_* flags the plan was made with

@@ -177,6 +177,25 @@ class Comm:
         self.ctx.check(self.ctx.lib.mdim_allreduce(self.ctx.handle, C.c_void_p(storage.dptr), storage.n, storage.dtype, code))
         return storage
 
+    def fold_sharded_axis(self, local_rows, n_rows_local, n_cols, op, init, out=None):
+        """`mdim_fold_sharded_axis`: the fold over the SHARDED (outermost) axis, bit-identical to the reference's sequential
+        chain, as one fused kernel per GPU that hands the running values from rank to rank over NVLink (csrc/k_fold_ring.cu).
+        `local_rows`: this rank's rows, a device-resident Storage of n_rows_local x n_cols elements; `op`: ops.Add / Sub / Mul /
+        BitAnd / BitOr / BitXor; -> the Storage of the n_cols results (on every rank).  Asynchronous on the context's stream."""
+        import ctypes as C
+        from . import lowering as L
+        if local_rows.n != n_rows_local * n_cols:
+            raise F.Panic(F.ERR_SIZE, "fold_sharded_axis: the block must hold n_rows_local x n_cols elements")
+        out = out or Storage.device(self.ctx, local_rows.dtype, n_cols)
+        imm = F.Scalar()
+        imm.u64 = L.imm_bits(local_rows.dtype, init)
+        self.ctx.check(self.ctx.lib.mdim_fold_sharded_axis(self.ctx.handle, C.c_void_p(local_rows.dptr), n_rows_local, n_cols, local_rows.dtype, op.code, imm,
+                                                           C.c_void_p(out.dptr)))
+        return out
+
+    def fold_status(self):
+        self.ctx.check(self.ctx.lib.mdim_fold_sharded_axis_status(self.ctx.handle))
+
     def peer_table(self, dptr, nbytes):
         import ctypes as C
         peers = (C.c_void_p * F.MAX_PEERS)()

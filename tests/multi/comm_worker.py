@@ -70,6 +70,19 @@ def main():
     exact = shard_view(fold_rows(whole.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize)), (usize, usize), usize, Add, np.float32(0)), rank, world)
     out["fold_exact"] = exact.collect(location="device", ctx=ctx).as_ref()
 
+    # (4') the same fold as ONE fused kernel per GPU, pipelined through the ranks: bit-exact AND replicated on every rank
+    ring = comm.fold_sharded_axis(A.storage, ib, J * K, Add, np.float32(0))
+    comm.fold_status()
+    out["fold_ring"] = ring.to_numpy()
+    a64 = (a.astype(np.float64) * 3.0)[rank * ib * J * K:(rank + 1) * ib * J * K]
+    A64 = Array.new((usize, usize), (ib, J * K), a64, "f64").to_device(ctx)
+    out["fold_ring_f64_mul_init"] = comm.fold_sharded_axis(A64.storage, ib, J * K, P.Mul, 0.5).to_numpy()
+    comm.fold_status()
+    odd_vals = np.random.default_rng([7, rank]).integers(0, 1 << 40, ib * 1028).astype(np.uint64)   # 1028 columns: a ragged last slice
+    odd = Array.new((usize, usize), (ib, 1028), odd_vals, usize).to_device(ctx)
+    out["fold_ring_u64_xor"] = comm.fold_sharded_axis(odd.storage, ib, 1028, P.BitXor, 0).to_numpy()
+    comm.fold_status()
+
     # (5) all-reduce with the other operators / dtypes
     mine_vals = np.array([rank + 1, 10 - rank, 7], dtype=np.int64)
     for op in ("sum", "prod", "min", "max"):

@@ -53,6 +53,17 @@ def test_c_abi_collectives_and_peer_tables(world, tmp_path):
     for p in parts:  # reassociated across ranks: the north star's 1e-6 relative tolerance
         assert np.max(np.abs(p["fold_allreduce"] - seq) / np.abs(seq)) <= 1e-6
     assert_same_bits(np.concatenate([p["fold_exact"] for p in parts]), seq, "peer-mapped fold over the sharded axis (bit-exact)")
+    seq64 = np.full(J * K, 0.5)
+    for i in range(I):
+        seq64 = seq64 * (a.astype(np.float64) * 3.0).reshape(I, J * K)[i]
+    ib = I // world
+    want_xor = np.zeros(1028, np.uint64)
+    for r in range(world):
+        want_xor ^= np.bitwise_xor.reduce(np.random.default_rng([7, r]).integers(0, 1 << 40, ib * 1028).astype(np.uint64).reshape(ib, 1028), axis=0)
+    for p in parts:  # the ring fold is bit-exact and replicated
+        assert_same_bits(p["fold_ring"], seq, "ring fold over the sharded axis (f32 add)")
+        assert_same_bits(p["fold_ring_f64_mul_init"], seq64, "ring fold (f64 mul, init 0.5)")
+        assert_same_bits(p["fold_ring_u64_xor"], want_xor, "ring fold (u64 xor, ragged slice)")
     ranks = np.arange(world)
     for p in parts:
         assert p["ar_sum"].tolist() == [int((ranks + 1).sum()), int((10 - ranks).sum()), 7 * world]
@@ -76,3 +87,27 @@ def test_cpp_mirror_runs_the_two_gpu_transpose(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "0 failures" in o, f"rank {r}:\n{o[-2000:]}"
+
+
+@pytest.mark.gpu
+def test_ring_fold_single_rank_is_the_sequential_fold():
+    """world = 1: the pipelined fold kernel alone (TMA row tiles through the shared-memory ring, sequential adds), no peers."""
+    import multidimension_b200 as P
+    from multidimension_b200 import _ffi as F
+    from multidimension_b200.runtime import Storage
+    from multidimension_b200.sharding import Comm
+    ctx = P.Context(0)
+    comm = Comm(ctx, 0, 1, Comm.unique_id())
+    rng = np.random.default_rng(11)
+    for rows, cols, dt, npdt in ((100, 4096, F.F32, np.float32), (33, 1028, F.F32, np.float32), (257, 516, F.F64, np.float64), (1, 8, F.F32, np.float32)):
+        x = rng.uniform(0, 1, rows * cols).astype(npdt)
+        st = Storage.device(ctx, dt, rows * cols)
+        ctx.upload(st.dptr, x)
+        got = comm.fold_sharded_axis(st, rows, cols, P.Add, npdt(0.25)).to_numpy()
+        comm.fold_status()
+        want = np.full(cols, npdt(0.25))
+        for i in range(rows):
+            want = want + x.reshape(rows, cols)[i]
+        assert_same_bits(got, want, f"ring fold {rows}x{cols}")
+    comm.close()
+    ctx.close()
