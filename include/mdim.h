@@ -119,7 +119,8 @@ typedef union mdim_scalar {
 /*
  * One node of the expression, nodes are stored in POST-ORDER (children before parent, left to
  * right), so the array is also a stack program.  Arity: LEAF/IOTA/CONST 0, UNARY 1, BINARY 2,
- * DIAG 1, GATHER n_comp, FOLD 1, CONCAT 2.  The last node is the root and its dtype is the output dtype.
+ * DIAG 1, GATHER n_comp, FOLD 1 (2 when n_comp == 2: the FIRST child is then the initial value, any value tree over
+ * the output axes — `let mut s = init.at(i)` — and `imm` is unused), CONCAT 2.  The last node is the root and its dtype is the output dtype.
  *
  * Iteration axes: 0..rank-1 are the output leaf axes, rank..rank+red_rank-1 the reduction axes.
  * Only nodes below a FOLD may have non-zero strides on reduction axes.
@@ -128,7 +129,7 @@ typedef struct mdim_node {
     int32_t kind;      /* mdim_node_kind */
     int32_t dtype;     /* result dtype of this node */
     int32_t op;        /* BINARY: mdim_binary_op; UNARY: mdim_unary_op; FOLD: mdim_binary_op */
-    int32_t n_comp;    /* GATHER: number of index components (= children); DIAG: number of pairs */
+    int32_t n_comp;    /* GATHER: number of index components (= children); DIAG: number of pairs; FOLD: 2 = (init, body) children */
     int32_t src_dtype; /* UNARY/CAST: dtype of the operand */
     int32_t n_peers;   /* LEAF/GATHER: 0/1 = `data` is one buffer; k>1 = the source Array is split into k
                           equal blocks of `peer_block` elements along its linear index, block p at

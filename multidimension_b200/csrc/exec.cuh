@@ -532,7 +532,8 @@ MDIM_FN void report(const Program& P, ErrWord* err, uint64_t pos, int status, in
 // depth change of one instruction
 MDIM_FN int depth_delta(int opc, int aux) {
     switch (opc) {
-        case OPC_LEAF_VEC: case OPC_LEAF_BCAST: case OPC_LEAF_STRIDED: case OPC_IOTA: case OPC_CONST: case OPC_FOLD_BEGIN: return 1;
+        case OPC_FOLD_BEGIN: return aux == 1 ? 0 : 1;  // aux 1: the initial value is already on the stack (FOLD with an init view)
+        case OPC_LEAF_VEC: case OPC_LEAF_BCAST: case OPC_LEAF_STRIDED: case OPC_IOTA: case OPC_CONST: return 1;
         case OPC_BINARY: case OPC_FOLD_STEP: case OPC_SELECT2: return -1;
         case OPC_GATHER: return 1 - aux;
         default: return 0;
@@ -715,8 +716,10 @@ MDIM_FN int exec_instr(const Program& P, ErrWord* err, int opc, int dtype, int o
             break;
         case OPC_FOLD_BEGIN:  // let mut s = init;  (the closure of rows().map(..))
             if constexpr (D < MAXD) {
+                if (aux != 1) {
 #pragma unroll
-                for (int l = 0; l < V; ++l) st[D][l] = (S)imm;
+                    for (int l = 0; l < V; ++l) st[D][l] = (S)imm;
+                }
 #pragma unroll
                 for (int a = 0; a < MAXR; ++a)
                     if (a >= MDIM_SHAPE_OF(P).rank) ts.c[a] = 0;
@@ -768,7 +771,7 @@ template <class Sig> MDIM_CE int sig_addr_slot(int pc) {
 }
 MDIM_CE int sig_depth_after(SigInstr I, int d) {
     return d + (I.opc == OPC_LEAF_VEC || I.opc == OPC_LEAF_BCAST || I.opc == OPC_LEAF_STRIDED || I.opc == OPC_IOTA || I.opc == OPC_CONST ||
-                        I.opc == OPC_FOLD_BEGIN ? 1
+                        (I.opc == OPC_FOLD_BEGIN && I.aux != 1) ? 1
                 : I.opc == OPC_BINARY || I.opc == OPC_FOLD_STEP || I.opc == OPC_SELECT2 ? -1
                 : I.opc == OPC_GATHER ? 1 - (int)I.aux
                                       : 0);
@@ -782,6 +785,7 @@ MDIM_FN void run_static(const Program& P, ErrWord* err, S (&st)[MAXD][V], Thread
         constexpr SigInstr I = Sig::code[PC];
         if constexpr (I.opc == OPC_FOLD_BEGIN) {
             constexpr int END = sig_fold_end<Sig>(PC);
+            constexpr int B = I.aux == 1 ? D - 1 : D;  // stack slot of the accumulator (aux 1: the init view's value, already pushed)
             exec_instr<D, S, V, MAXD, WIDE, MAXR>(P, err, I.opc, I.dtype, I.op, I.aux, PC, st, ts);
             constexpr SigInstr E = Sig::code[END < Sig::n ? END : PC];
             // Outer loop: the slower reduction axes (coordinates in c[], rare).  Inner loop: the fastest one,
@@ -792,20 +796,20 @@ MDIM_FN void run_static(const Program& P, ErrWord* err, S (&st)[MAXD][V], Thread
 #pragma unroll 8
                 for (uint64_t k = 0; k < MDIM_SHAPE_OF(P).red_fast_len; ++k) {
                     ts.rk = (typename CoordTraits<WIDE>::coord_t)k;
-                    run_static<Sig, PC + 1, D + 1, END, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
-                    if constexpr (D + 2 <= MAXD) {
+                    run_static<Sig, PC + 1, B + 1, END, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
+                    if constexpr (B >= 0 && B + 2 <= MAXD) {
 #pragma unroll
                         for (int l = 0; l < V; ++l) {
                             bool arith = false;
-                            st[D][l] = bin_op<S>(E.dtype, E.op, E.aux, st[D][l], st[D + 1][l], arith);
-                            if (arith && ((ts.mask >> l) & 1u)) report(P, err, ts.pos0 + l, MDIM_ERR_ARITH, P.instr[END].n, 0, (uint64_t)st[D + 1][l], 0);
+                            st[B][l] = bin_op<S>(E.dtype, E.op, E.aux, st[B][l], st[B + 1][l], arith);
+                            if (arith && ((ts.mask >> l) & 1u)) report(P, err, ts.pos0 + l, MDIM_ERR_ARITH, P.instr[END].n, 0, (uint64_t)st[B + 1][l], 0);
                         }
                     }
                 }
                 ts.rk = 0;
                 carry_red<WIDE, MAXR>(P, ts);
             }
-            run_static<Sig, END + 1, D + 1, STOP, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
+            run_static<Sig, END + 1, B + 1, STOP, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
         } else {
             exec_instr<D, S, V, MAXD, WIDE, MAXR, sig_addr_slot<Sig>(PC)>(P, err, I.opc, I.dtype, I.op, I.aux, PC, st, ts);
             run_static<Sig, PC + 1, sig_depth_after(I, D), STOP, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);

@@ -48,7 +48,8 @@ static bool is_float(int dt) { return dt == MDIM_F32 || dt == MDIM_F64; }
 static int node_arity(const mdim_node& n) {
     switch (n.kind) {
         case MDIM_NODE_LEAF: case MDIM_NODE_IOTA: case MDIM_NODE_CONST: return 0;
-        case MDIM_NODE_UNARY: case MDIM_NODE_DIAG: case MDIM_NODE_FOLD: return 1;
+        case MDIM_NODE_UNARY: case MDIM_NODE_DIAG: return 1;
+        case MDIM_NODE_FOLD: return n.n_comp == 2 ? 2 : 1;  // (init, body) or body alone (init = imm)
         case MDIM_NODE_BINARY: case MDIM_NODE_CONCAT: return 2;
         case MDIM_NODE_GATHER: return n.n_comp;
     }
@@ -147,8 +148,9 @@ int Builder::validate() {
             case MDIM_NODE_FOLD: {
                 if (n.op < 0 || n.op >= MDIM_BINARY_COUNT) return why.fail(MDIM_ERR_INVALID, "node %d: bad binary op", i);
                 const int l = n.kind == MDIM_NODE_BINARY ? e->nodes[child[i][0]].dtype : n.dtype;
-                const int r = e->nodes[child[i][n.kind == MDIM_NODE_BINARY ? 1 : 0]].dtype;
+                const int r = e->nodes[child[i][k - 1]].dtype;  // BINARY: the right operand; FOLD: the body (its last child)
                 if (l != n.dtype) return why.fail(MDIM_ERR_INVALID, "node %d: lhs dtype mismatch", i);
+                if (n.kind == MDIM_NODE_FOLD && k == 2 && e->nodes[child[i][0]].dtype != n.dtype) return why.fail(MDIM_ERR_INVALID, "node %d: fold init dtype mismatch", i);
                 if (n.op == MDIM_SHL || n.op == MDIM_SHR) { if (!is_int(l) || !is_int(r)) return why.fail(MDIM_ERR_INVALID, "node %d: shift on a float", i); }
                 else if (r != n.dtype) return why.fail(MDIM_ERR_INVALID, "node %d: rhs dtype mismatch", i);
                 if (is_float(n.dtype) && n.op >= MDIM_AND) return why.fail(MDIM_ERR_INVALID, "node %d: bit op on a float", i);
@@ -177,7 +179,7 @@ int Builder::validate() {
     // mark nodes under the fold: post-order => the fold's subtree is a contiguous range ending at it
     for (int i = 0; i < e->n_nodes; ++i) under_fold[i] = false;
     if (fold_node >= 0) {
-        std::vector<int> work{child[fold_node][0]};
+        std::vector<int> work{child[fold_node][n_child[fold_node] - 1]};  // the body; an init view (first child) lives outside the loop
         while (!work.empty()) {
             int x = work.back(); work.pop_back();
             under_fold[x] = true;
@@ -252,7 +254,7 @@ int Builder::push_instr(const Instr& in) {
     if (P.n_instr >= kMaxInstr) return why.fail(MDIM_ERR_UNSUPPORTED, "expression too long (> %d device instructions)", kMaxInstr);
     P.instr[P.n_instr++] = in;
     depth += in.opc == OPC_LEAF_VEC || in.opc == OPC_LEAF_BCAST || in.opc == OPC_LEAF_STRIDED || in.opc == OPC_IOTA || in.opc == OPC_CONST ||
-                     in.opc == OPC_FOLD_BEGIN ? 1
+                     (in.opc == OPC_FOLD_BEGIN && in.aux != 1) ? 1
              : in.opc == OPC_BINARY || in.opc == OPC_FOLD_STEP || in.opc == OPC_SELECT2 ? -1
              : in.opc == OPC_GATHER ? 1 - (int)in.aux
                                     : 0;
@@ -425,15 +427,20 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
             return push_instr(in);
         }
         case MDIM_NODE_FOLD: {
+            const int body = child[ni][n_child[ni] - 1];
+            if (n_child[ni] == 2) {  // `let mut s = init.at(i)`: the init value is on the stack when the loop starts
+                int st0 = gen(child[ni][0], mask_first, mask_n); if (st0) return st0;
+                in.aux = 1;
+            }
             in.opc = OPC_FOLD_BEGIN; in.imm = n.imm.u64;
             if (dtype_size(n.dtype) == 4) in.imm &= 0xffffffffull;
             if (dtype_size(n.dtype) == 1) in.imm &= 0xffull;
             int st = push_instr(in); if (st) return st;
             const int begin_pc = P.n_instr - 1;
             const int body_pc = P.n_instr;
-            st = gen(child[ni][0], mask_first, mask_n); if (st) return st;
+            st = gen(body, mask_first, mask_n); if (st) return st;
             Instr s; memset(&s, 0, sizeof s);
-            s.opc = OPC_FOLD_STEP; s.dtype = (uint8_t)n.dtype; s.op = (uint8_t)n.op; s.aux = (uint8_t)e->nodes[child[ni][0]].dtype;
+            s.opc = OPC_FOLD_STEP; s.dtype = (uint8_t)n.dtype; s.op = (uint8_t)n.op; s.aux = (uint8_t)e->nodes[body].dtype;
             s.slot = (uint16_t)body_pc; s.n = (uint16_t)ni;
             st = push_instr(s); if (st) return st;
             P.instr[begin_pc].slot = (uint16_t)P.n_instr;
@@ -606,7 +613,7 @@ int Builder::detect_fast_paths() {
     }
     // (2) last-axis sequential fold of one contiguous f32/f64/int leaf, optionally fused with
     //     `x (eop) (fold [post_op c])` broadcast back over the folded axis (config C4)
-    if (fold_node >= 0 && red_rank == 1 && rank <= 2 && !plan->wide && !(flags & kPlanScalarOut)) {
+    if (fold_node >= 0 && n_child[fold_node] == 1 && red_rank == 1 && rank <= 2 && !plan->wide && !(flags & kPlanScalarOut)) {
         const mdim_node& F = N[fold_node];
         const int fc = child[fold_node][0];
         const uint64_t row_len = len[n_axes - 1];

@@ -268,6 +268,8 @@ def emit(root, axes, location):
             d.axis_c[0] = n.pairs[0][1]
         if n.kind in (F.CONST, F.FOLD):
             d.imm.u64 = imm_bits(n.dtype, n.imm)
+        if n.kind == F.FOLD and len(n.children) == 2:  # (init view, body): `let mut s = init.at(i)`
+            d.n_comp = 2
     e = F.Expr()
     e.abi_version = F.ABI_VERSION
     e.rank = len(axes)

@@ -59,7 +59,9 @@ class Cast:
 
 
 class Fold:
-    """`|row| { let mut s = init; row.each(|x| s = B::call(s, x)); s }` — sequential, index order."""
+    """`|row| { let mut s = init; row.each(|x| s = B::call(s, x)); s }` — sequential, index order.
+    `init` is a scalar, or a View indexed like `rows()` (then row i starts from `init.at(i)`: what lets a fold be continued
+    from another fold's result, e.g. rank r of a sharded axis continuing rank r-1's running values)."""
 
     def __init__(self, B, init):
         self.B, self.init = B, init

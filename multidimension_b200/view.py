@@ -668,6 +668,18 @@ class Map(View):
         if isinstance(self.v, Rows):
             groups_i, groups_j, value = self.v._lower_rows()
             red = tuple(_flat(groups_j))
+            if isinstance(self.f.init, View):  # `let mut s = init.at(i)`: the initial value is a view over the rows' index
+                init = self.f.init
+                if init.I != self.v.I or init._size != self.v._size:
+                    raise Panic(F.ERR_SIZE, "Unequal sizes") if init.I == self.v.I else TypeError("Fold: the init view must be indexed like rows()")
+                if isinstance(init.T, tuple) or dtype_of(init.T) != value.dtype:
+                    raise TypeError("Fold: the init view's element type differs from the rows'")
+                gi, vi = init._lower()
+                tv, tw = {}, {}
+                groups_i = [_unify_group(a, b, tv, tw) for a, b in zip(groups_i, gi)]
+                value = _substituter(tv)(value)
+                node = L.Node(F.FOLD, value.dtype, op=self.f.B.code, children=(_substituter(tw)(vi), value), imm=0, red_axes=red)
+                return groups_i, node
             node = L.Node(F.FOLD, value.dtype, op=self.f.B.code, children=(value,), imm=self.f.init, red_axes=red)
             return groups_i, node
         groups, value = self.v._lower()

@@ -50,7 +50,8 @@ static int is_int(int dt) { return dt == MDIM_U8 || dt == MDIM_I32 || dt == MDIM
 static int arity(const mdim_node* n) {
     switch (n->kind) {
         case MDIM_NODE_LEAF: case MDIM_NODE_IOTA: case MDIM_NODE_CONST: return 0;
-        case MDIM_NODE_UNARY: case MDIM_NODE_DIAG: case MDIM_NODE_FOLD: return 1;
+        case MDIM_NODE_UNARY: case MDIM_NODE_DIAG: return 1;
+        case MDIM_NODE_FOLD: return n->n_comp == 2 ? 2 : 1; /* (init view, body) or body alone */
         case MDIM_NODE_BINARY: case MDIM_NODE_CONCAT: return 2;
         case MDIM_NODE_GATHER: return n->n_comp;
     }
@@ -336,13 +337,18 @@ static mdim_scalar at(oracle_t* o, int ni) {
         case MDIM_NODE_FOLD: { /* rows().map(|row| { let mut s = init; row.each(|x| s = s ⊕ x); s })
                                    src/view.rs:617-622,1341,250-252: sequential, in index order */
             int rank = o->e->rank, rr = o->e->red_rank;
+            int body = o->child[ni][n->n_comp == 2 ? 1 : 0];
             mdim_scalar acc = n->imm;
+            if (n->n_comp == 2) { /* `let mut s = init.at(i)`: the initial value is itself a view over the output index */
+                acc = at(o, o->child[ni][0]);
+                if (o->failed) return r;
+            }
             uint64_t count = 1;
             for (int a = 0; a < rr; ++a) count *= o->e->length[rank + a];
             for (int a = 0; a < rr; ++a) o->coord[rank + a] = 0;
-            int cdt = o->e->nodes[o->child[ni][0]].dtype;
+            int cdt = o->e->nodes[body].dtype;
             for (uint64_t k = 0; k < count; ++k) {
-                mdim_scalar x = at(o, o->child[ni][0]);
+                mdim_scalar x = at(o, body);
                 if (o->failed) return r;
                 acc = binary(o, ni, n->op, n->dtype, acc, x, cdt);
                 if (o->failed) return r;

@@ -805,6 +805,17 @@ def fn_view(I, size, f):  # src/view.rs:1436-1443
     return all_(I, size).map(f)
 
 
+def fold_rows_from(v, I, J, op, init_view):
+    """The same fold with a per-row initial value: `rows().zip(init).map(|(row, s0)| { let mut s = s0; row.each(..); s })`
+    (Zip of src/view.rs:1178-1198 over views indexed by I; each row starts from init_view.at(i))."""
+    def fold(pair):
+        row, s0 = pair
+        s = [s0]
+        row.each(lambda x: s.__setitem__(0, op(s[0], x)))
+        return s[0]
+    return v.rows(I, J).zip(init_view).map(fold)
+
+
 def fold_rows(v, I, J, op, init):
     """The reference's ONLY spelling of an axis fold (no reduce API exists):
         v.rows::<I,J>().map(|row| { let mut s = init; row.each(|x| s = op(s, x)); s })

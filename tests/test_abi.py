@@ -135,3 +135,43 @@ print(st, time.perf_counter() - t0, log.value.decode()[:200])
     env["HOME"] = env["XDG_CACHE_HOME"] = str(home)
     p = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=env, timeout=300)
     assert p.returncode == 0 and not os.listdir(home)
+
+
+def test_descriptor_limits_are_declined_cleanly():
+    """MDIM_MAX_NODES (48 nodes), the 56-instruction program, MDIM_MAX_RANK (8 axes) and the 12 array operands are hard
+    limits of one fused expression: beyond them the answer is MDIM_ERR_UNSUPPORTED with a message — from the host mirror,
+    from the planner given a hand-made descriptor, and from the oracle — never a crash or a silently wrong kernel."""
+    from helpers import oracle_collect, emu_collect, CheckerPanic
+    from multidimension_b200 import lowering as L
+    from multidimension_b200.view import _flat
+    a = Array.new(usize, 16, np.arange(16, dtype=np.float32))
+    v = a
+    for k in range(24):  # 1 + 2 * 24 = 49 nodes
+        v = v + Scalar(float(k), "f32")
+    with pytest.raises(P.Unsupported, match="49 nodes"):
+        v.describe()
+    ok = a
+    for k in range(23):  # 47 nodes: the largest chain of this shape that fits
+        ok = ok + Scalar(float(k), "f32")
+    assert ok.describe()
+    want = np.arange(16, dtype=np.float32)
+    for k in range(23):
+        want = want + np.float32(k)
+    assert np.array_equal(emu_collect(ok), want) and np.array_equal(oracle_collect(ok), want)
+    # a hand-made descriptor that lies about its size goes through the C ABI's own validation
+    groups, value = ok._lower()
+    em = L.emit(value, _flat(groups), "any")
+    em.expr.n_nodes = F.MAX_NODES + 1
+    buf = C.create_string_buffer(256)
+    assert F.lib().mdim_plan_describe_nodevice(C.byref(em.expr), 0, buf, 256) in (F.ERR_UNSUPPORTED, F.ERR_INVALID)
+    # rank: 9 position axes
+    nine = Array.new((((usize, usize, usize), (usize, usize, usize)), (usize, usize, usize)), (((2, 2, 2), (2, 2, 2)), (2, 2, 2)), np.zeros(512, np.float32))
+    with pytest.raises(P.Unsupported, match="9 position axes"):
+        nine.describe()
+    # operands: 13 distinct Arrays in one expression
+    many = a
+    for k in range(12):
+        many = many + Array.new(usize, 16, np.full(16, k, np.float32))
+    with pytest.raises((P.MdimError, CheckerPanic)) as e:
+        emu_collect(many)
+    assert e.value.status == F.ERR_UNSUPPORTED

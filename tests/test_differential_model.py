@@ -494,6 +494,12 @@ def op_fold(rng, v):
     p = rng.randint(0, max(len(L) - 1, 0))
     (I, _), (J, _) = random_tree(rng, L[:p]), random_tree(rng, L[p:])
     name, fn = rng.choice(BIN_OPS[:2] + ([BIN_OPS[2]] if v.T == "f32" else []))
+    def has_unit(t):
+        return t == () or (isinstance(t, tuple) and any(has_unit(x) for x in t))
+    if rng.random() < 0.35 and p > 0 and not has_unit(I):  # `let mut s = init.at(i)`: the initial value is a view indexed like rows()
+        init = fresh_array(rng, I, PX.to_iso_size(v.size, v.I, (I, J))[0], v.T, note="init")
+        return Both(M.fold_rows_from(v.m, mt(I), mt(J), fn, init.m), v.p.rows(I, J).map(P.Fold(getattr(P, name), init.p)), v.T,
+                    f"fold_rows<{I!r},{J!r}>({v.note}, {name}, init={init.note})")
     init = np.float32(0.25) if v.T == "f32" else 1
     return Both(M.fold_rows(v.m, mt(I), mt(J), fn, init if v.T == "f32" else int(init)), P.fold_rows(v.p, I, J, getattr(P, name), init), v.T,
                 f"fold_rows<{I!r},{J!r}>({v.note}, {name})")
