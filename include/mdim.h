@@ -37,6 +37,14 @@ extern "C" {
 #define MDIM_MAX_RANK 8   /* output leaf axes + reduction leaf axes */
 #define MDIM_MAX_NODES 48 /* nodes in one fused expression */
 #define MDIM_MAX_PEERS 8  /* shards of a peer-mapped gather source (one 8-GPU NVSwitch box) */
+#define MDIM_MAX_OUTS 4   /* scalar leaves of a tuple-typed element collected in ONE launch (MDIM_NODE_TUPLE) */
+
+/* Layout of tuple-typed Arrays.  Rust leaves the layout of (T, U) unspecified (no repr(C) on tuples), so the device
+ * declares its own: an Array whose element type is a tuple is a STRUCTURE OF ARRAYS — one dense row-major run per
+ * scalar leaf of the (flattened) element type, in flattening order, each exactly as a scalar-typed Array of that leaf
+ * type would be stored.  `Array<I, (usize, f32)>` is a u64 run of I::length elements and an f32 run of the same length;
+ * element k of the Array is (run0[k], run1[k]).  mdim_collect_tuple fills all runs from ONE kernel launch (shared operands
+ * are read once); a host `Vec<(T, U)>` is obtained by interleaving the downloaded runs (DeviceArray::to_raw). */
 
 /* ---- status codes: every reference panic site maps to one of these ---------- */
 typedef enum mdim_status {
@@ -103,7 +111,10 @@ typedef enum mdim_node_kind {
     MDIM_NODE_GATHER = 6, /* Compose<V,W>: src/view.rs:897-912; MapAxis: src/view.rs:1140-1170      */
     MDIM_NODE_FOLD = 7,   /* rows().map(|r| fold r.each(..)): src/view.rs:617-622,1330-1342,250-252 */
     MDIM_NODE_CONCAT = 8, /* Concat<V,W,I,J>: src/view.rs:920-946 (coord[axis_a[0]] < axis_c[0] ? V : W)  */
-    MDIM_NODE_KIND_COUNT = 9
+    MDIM_NODE_TUPLE = 9,  /* ROOT ONLY: a tuple-typed element — `zip` without an operator (ops::Pair, src/ops.rs:25-29), `enumerate`
+                             (src/view.rs:829-838), a compound All<I> (src/index.rs:177-186).  n_comp children (<= MDIM_MAX_OUTS),
+                             one per scalar leaf of the element type in flattening order; see "layout of tuple-typed Arrays" */
+    MDIM_NODE_KIND_COUNT = 10
 } mdim_node_kind;
 
 typedef union mdim_scalar {
@@ -220,6 +231,10 @@ int mdim_host_free(mdim_ctx* ctx, void* hptr);
  * the TMA transpose, 32-byte alignment the 256-bit stores (cudaMalloc gives 256).  An output that is only
  * element-aligned (a slice of a caller's tensor) is written with scalar stores. */
 int mdim_collect(mdim_ctx* ctx, const mdim_expr* e, void* out_device, uint32_t flags);
+
+/* View::collect of a tuple-typed view: `e`'s root is an MDIM_NODE_TUPLE with n_outs children; outs_device[c] receives the run
+ * of scalar leaf c (see "layout of tuple-typed Arrays").  One kernel launch; same flags, errors and alignment rules. */
+int mdim_collect_tuple(mdim_ctx* ctx, const mdim_expr* e, void* const* outs_device, int n_outs, uint32_t flags);
 
 /* Same, but every LEAF/GATHER `data` pointer and `out` are HOST buffers: uploads, collects and
  * downloads, chunked along the outermost axis and pipelined over copy/compute streams when the

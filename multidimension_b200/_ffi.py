@@ -29,7 +29,8 @@ ADD, SUB, MUL, DIV, REM, AND, OR, XOR, SHL, SHR = range(10)
 # unary ops (mdim_unary_op)
 NEG, NOT, ABS, SQRT, CAST = range(5)
 # node kinds
-LEAF, IOTA, CONST, UNARY, BINARY, DIAG, GATHER, FOLD, CONCAT = range(9)
+LEAF, IOTA, CONST, UNARY, BINARY, DIAG, GATHER, FOLD, CONCAT, TUPLE = range(10)
+MAX_OUTS = 4
 
 COLLECT_ASYNC, COLLECT_NO_FASTPATH, COLLECT_NO_STATIC, COLLECT_NO_JIT = 1, 2, 4, 8
 IPC_HANDLE_BYTES = 64
@@ -86,6 +87,7 @@ SYMBOLS = [
     ("mdim_host_free", C.c_int, [_P, _P]),
     ("mdim_collect", C.c_int, [_P, C.POINTER(Expr), _P, C.c_uint32]),
     ("mdim_collect_host", C.c_int, [_P, C.POINTER(Expr), _P, C.c_uint32]),
+    ("mdim_collect_tuple", C.c_int, [_P, C.POINTER(Expr), _PP, C.c_int, C.c_uint32]),
     ("mdim_plan_describe", C.c_int, [_P, C.POINTER(Expr), C.c_uint32, C.c_char_p, C.c_size_t]),
     ("mdim_plan_describe_nodevice", C.c_int, [C.POINTER(Expr), C.c_uint32, C.c_char_p, C.c_size_t]),
     ("mdim_ipc_export", C.c_int, [_P, _P, C.POINTER(C.c_uint8)]),

@@ -101,14 +101,15 @@ bool may_skip_wait(mdim_ctx* ctx, const Plan& p, const void* out) {
     if (p.n_in_ranges >= 0)
         for (int i = 0; i < p.n_in_ranges; ++i) mine[n++] = {p.in_range[i].lo, p.in_range[i].hi, false};
     mine[n++] = {(uint64_t)(uintptr_t)out, (uint64_t)(uintptr_t)out + p.out_elems * (uint64_t)p.out_esize, true};
-    bool conflict = !usable || ctx->inflight.size() + (size_t)n > 256;
+    bool conflict = !usable || ctx->inflight.size() + (size_t)n > 256 || p.n_out > 1;  // several output runs: simply wait
     for (size_t k = 0; k < ctx->inflight.size() && !conflict; ++k) {
         const mdim_ctx::Touched& t = ctx->inflight[k];
         for (int i = 0; i < n; ++i)
             if ((t.write || mine[i].write) && mine[i].lo < t.hi && t.lo < mine[i].hi) { conflict = true; break; }
     }
     if (conflict) ctx->inflight.clear();  // this kernel waits, so everything before it will have completed
-    if (usable) ctx->inflight.insert(ctx->inflight.end(), mine, mine + n);
+    if (p.n_out > 1) ctx->inflight.push_back({0, ~0ull, true});  // (its other runs are not in `mine`: conflicts with everything)
+    else if (usable) ctx->inflight.insert(ctx->inflight.end(), mine, mine + n);
     else if (p.n_in_ranges < 0) ctx->inflight.push_back({0, ~0ull, true});  // untracked operands: conflicts with everything
     return !conflict;
 }
@@ -440,6 +441,7 @@ int mdim_collect(mdim_ctx* ctx, const mdim_expr* e, void* out_device, uint32_t f
     int st = plan_expr(e, flags, plan, why, sizeof why);
     if (st) { delete plan; return set_error(ctx, st, why); }
     if (plan->kind != KK_EMPTY && !out_device) { delete plan; return set_error(ctx, MDIM_ERR_INVALID, "null output buffer"); }
+    if (plan->kind != KK_EMPTY && plan->n_out > 1) { delete plan; return set_error(ctx, MDIM_ERR_INVALID, "a tuple-typed root needs mdim_collect_tuple (one output run per scalar leaf)"); }
     if (plan->kind != KK_EMPTY && ((uintptr_t)out_device % (uintptr_t)plan->out_esize) != 0) { delete plan; return set_error(ctx, MDIM_ERR_INVALID, "output buffer is not aligned to its element size"); }
     if (plan->kind != KK_EMPTY && ((uintptr_t)out_device % 16) != 0 && (plan->vec > 1 || plan->kind == KK_FOLD_ROWS)) {
         // an element-aligned output (a slice of a caller's tensor): plan again with scalar stores
@@ -449,6 +451,32 @@ int mdim_collect(mdim_ctx* ctx, const mdim_expr* e, void* out_device, uint32_t f
     cudaError_t ce = cudaSetDevice(ctx->device);
     if (ce != cudaSuccess) { delete plan; return cuda_fail(ctx, ce, "cudaSetDevice"); }
     st = collect_planned(ctx, plan, out_device, flags);
+    delete plan;
+    return st;
+}
+
+int mdim_collect_tuple(mdim_ctx* ctx, const mdim_expr* e, void* const* outs_device, int n_outs, uint32_t flags) {
+    if (!ctx || !outs_device || n_outs < 1 || n_outs > MDIM_MAX_OUTS) return MDIM_ERR_INVALID;
+    Plan* plan = new (std::nothrow) Plan();
+    if (!plan) return MDIM_ERR_NOMEM;
+    char why[160];
+    int st = plan_expr(e, flags, plan, why, sizeof why);
+    if (st) { delete plan; return set_error(ctx, st, why); }
+    if (plan->kind == KK_EMPTY) { delete plan; return MDIM_OK; }
+    if (plan->n_out != n_outs) { delete plan; return set_error(ctx, MDIM_ERR_INVALID, "the number of output runs does not match the TUPLE root"); }
+    bool aligned16 = true;
+    for (int k = 0; k < n_outs; ++k) {
+        if (!outs_device[k] || ((uintptr_t)outs_device[k] % (uintptr_t)plan->out_esizes[k]) != 0) { delete plan; return set_error(ctx, MDIM_ERR_INVALID, "null or misaligned output run"); }
+        aligned16 = aligned16 && ((uintptr_t)outs_device[k] % 16) == 0;
+    }
+    if (!aligned16 && plan->vec > 1) {
+        st = plan_expr(e, flags | kPlanScalarOut, plan, why, sizeof why);
+        if (st) { delete plan; return set_error(ctx, st, why); }
+    }
+    for (int k = 1; k < n_outs; ++k) plan->prog.out_more[k - 1] = outs_device[k];
+    cudaError_t ce = cudaSetDevice(ctx->device);
+    if (ce != cudaSuccess) { delete plan; return cuda_fail(ctx, ce, "cudaSetDevice"); }
+    st = collect_planned(ctx, plan, outs_device[0], flags);
     delete plan;
     return st;
 }

@@ -878,6 +878,12 @@ MDIM_FN void eval_vector(const Program& P, void* out, ErrWord* err, uint64_t g) 
         if constexpr (Sig::n > 0) run_static<Sig, 0, 0, Sig::n, S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
         else run_interp<S, V, MAXD, WIDE, MAXR>(P, err, st, ts);
         st_vector<S, V>(out, ts.pos0, esize_of(MDIM_SHAPE_OF(P).out_dtype), st[0], MDIM_STORE_STREAMING, (P.flags & PF_VEC256) != 0);
+        if (MDIM_SHAPE_OF(P).n_out > 1) {  // a tuple-typed root: value k of the final stack is scalar leaf k, stored to its own run
+#pragma unroll
+            for (int k = 1; k < MDIM_MAX_OUTS; ++k)
+                if (k < MAXD && k < MDIM_SHAPE_OF(P).n_out)
+                    st_vector<S, V>(P.out_more[k - 1], ts.pos0, esize_of(MDIM_SHAPE_OF(P).out_dtypes[k]), st[k < MAXD ? k : 0], MDIM_STORE_STREAMING, false);
+        }
         if constexpr (VPT > 1) {
             ts.c[0] += (coord_t)V;
             ts.pos0 += (uint64_t)V;

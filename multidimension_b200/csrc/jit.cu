@@ -84,6 +84,7 @@ std::string make_shape_source(const Program& P) {
     auto set = [&](const char* fmt, auto... args) { snprintf(b, sizeof b, fmt, args...); s += b; };
     set("p.rank=%d; p.red_rank=%d; p.n_instr=%d; p.n_addr=%d; p.n_pred=%d; p.out_dtype=%d; p.vec=%d; p.vpt=%d;\n", P.rank, P.red_rank, P.n_instr, P.n_addr,
         P.n_pred, P.out_dtype, P.vec, P.vpt);
+    set("p.n_out=%d; p.out_dtypes[0]=%d; p.out_dtypes[1]=%d; p.out_dtypes[2]=%d; p.out_dtypes[3]=%d;\n", P.n_out, P.out_dtypes[0], P.out_dtypes[1], P.out_dtypes[2], P.out_dtypes[3]);
     set("p.n_vec=%lluull; p.red_count=%lluull; p.red_fast_len=%lluull;\n", (unsigned long long)P.n_vec, (unsigned long long)P.red_count,
         (unsigned long long)P.red_fast_len);
     for (int a = 0; a < kMaxRank; ++a)
@@ -144,6 +145,7 @@ std::string shape_key(const Program& P) {
     for (int i = 0; i < kMaxInstr; ++i) q.instr[i].imm = 0;
     for (int i = 0; i < kMaxAddr; ++i) { q.addr[i].ptr = nullptr; q.addr[i].offset = 0; }
     memset(&q.peers, 0, sizeof q.peers);
+    memset(q.out_more, 0, sizeof q.out_more);
     return std::string((const char*)&q, sizeof q);
 }
 

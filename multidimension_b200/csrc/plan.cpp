@@ -52,6 +52,7 @@ static int node_arity(const mdim_node& n) {
         case MDIM_NODE_FOLD: return n.n_comp == 2 ? 2 : 1;  // (init, body) or body alone (init = imm)
         case MDIM_NODE_BINARY: case MDIM_NODE_CONCAT: return 2;
         case MDIM_NODE_GATHER: return n.n_comp;
+        case MDIM_NODE_TUPLE: return n.n_comp;
     }
     return -1;
 }
@@ -111,6 +112,11 @@ int Builder::validate() {
         const int k = node_arity(n);
         if (k < 0 || k > sp) return why.fail(MDIM_ERR_INVALID, "node %d: arity %d with %d operands available", i, k, sp);
         if (n.kind == MDIM_NODE_GATHER && (k < 1 || k > 3)) return why.fail(k < 1 ? MDIM_ERR_INVALID : MDIM_ERR_UNSUPPORTED, "node %d: gather with %d components", i, k);
+        if (n.kind == MDIM_NODE_TUPLE) {
+            if (i != e->n_nodes - 1) return why.fail(MDIM_ERR_INVALID, "node %d: a TUPLE node must be the root", i);
+            if (k < 1) return why.fail(MDIM_ERR_INVALID, "node %d: empty tuple", i);
+            if (k > MDIM_MAX_OUTS) return why.fail(MDIM_ERR_UNSUPPORTED, "a tuple-typed element with %d scalar leaves (> %d): collect the leaves separately", k, MDIM_MAX_OUTS);
+        }
         n_child[i] = k;
         for (int c = 0; c < k; ++c) child[i][c] = stack[sp - k + c];
         sp -= k;
@@ -426,6 +432,9 @@ int Builder::gen(int ni, int mask_first, int mask_n) {
             in.opc = OPC_GATHER; in.slot = (uint16_t)slot; in.aux = (uint8_t)n.n_comp; in.n = (uint16_t)ni;
             return push_instr(in);
         }
+        case MDIM_NODE_TUPLE:  // no instruction: the children's values are left on the stack in order, value k is output k
+            for (int c = 0; c < n_child[ni]; ++c) { int st = gen(child[ni][c], mask_first, mask_n); if (st) return st; }
+            return MDIM_OK;
         case MDIM_NODE_FOLD: {
             const int body = child[ni][n_child[ni] - 1];
             if (n_child[ni] == 2) {  // `let mut s = init.at(i)`: the init value is on the stack when the loop starts
@@ -466,7 +475,12 @@ int Builder::emit() {
     memset(&P, 0, sizeof P);
     const int root = e->n_nodes - 1;
     P.rank = rank; P.red_rank = red_rank;
-    P.out_dtype = e->nodes[root].dtype;
+    const bool tuple_root = e->nodes[root].kind == MDIM_NODE_TUPLE;
+    P.n_out = tuple_root ? n_child[root] : 1;
+    for (int k = 0; k < P.n_out; ++k) P.out_dtypes[k] = tuple_root ? e->nodes[child[root][k]].dtype : e->nodes[root].dtype;
+    P.out_dtype = P.out_dtypes[0];
+    plan->n_out = P.n_out;
+    for (int k = 0; k < P.n_out; ++k) plan->out_esizes[k] = dtype_size(P.out_dtypes[k]);
     for (int g = 0; g < n_axes; ++g) P.length[pa(g)] = len[g];
     P.red_fast_len = 1;
     if (red_rank > 0) { P.red_fast_len = len[n_axes - 1]; P.length[pa(n_axes - 1)] = 1; }
@@ -547,7 +561,7 @@ int Builder::emit() {
     plan->vec256_ok = (V * slot == 32) ? 1 : 0;
     int st = gen(root, 0, 0);
     if (st) return st;
-    if (depth != 1) return why.fail(MDIM_ERR_INVALID, "internal: program leaves depth %d", depth);
+    if (depth != P.n_out) return why.fail(MDIM_ERR_INVALID, "internal: program leaves depth %d", depth);
     if (max_depth > kMaxDepth) return why.fail(MDIM_ERR_UNSUPPORTED, "expression needs a value stack of %d (> %d)", max_depth, kMaxDepth);
     plan->max_depth = max_depth;
     // signature bytes
@@ -558,6 +572,10 @@ int Builder::emit() {
         plan->sig[plan->sig_len++] = (char)P.instr[i].op;
         plan->sig[plan->sig_len++] = (char)P.instr[i].aux;
     }
+    if (P.n_out > 1) {  // several outputs: no pre-built signature may match, and the run-time specialisation is keyed on the count
+        plan->sig[plan->sig_len++] = (char)0xFE; plan->sig[plan->sig_len++] = (char)P.n_out;
+        plan->sig[plan->sig_len++] = 0; plan->sig[plan->sig_len++] = 0;
+    }
     return MDIM_OK;
 }
 
@@ -566,6 +584,7 @@ int Builder::detect_fast_paths() {
     Program& P = plan->prog;
     const mdim_node* N = e->nodes;
     const int root = e->n_nodes - 1;
+    if (N[root].kind == MDIM_NODE_TUPLE) return MDIM_OK;  // several outputs: the evaluator only
     // (1) tiled transpose: a single leaf whose unit-stride axis is not the output's innermost axis
     if (e->n_nodes == 1 && N[0].kind == MDIM_NODE_LEAF && red_rank == 0 && rank >= 2) {
         const int es = dtype_size(N[0].dtype);

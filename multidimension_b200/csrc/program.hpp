@@ -88,6 +88,9 @@ struct Program {
     int32_t red_rank;  // coalesced reduction axes
     int32_t n_instr, n_addr, n_pred;
     int32_t out_dtype;
+    int32_t n_out;            // 1, or the number of scalar leaves of a tuple-typed root (MDIM_NODE_TUPLE): value k of the final stack goes to out k
+    int32_t out_dtypes[MDIM_MAX_OUTS];
+    void* out_more[MDIM_MAX_OUTS - 1];  // run-time: the output runs 1.. (run 0 is the kernel's `out` argument)
     int32_t vec;  // lanes per vector along the innermost output axis (program axis 0)
     int32_t vpt;  // consecutive vectors per thread trip along that axis
     int32_t pad0;
@@ -206,6 +209,8 @@ struct Plan {
     int32_t static_id;   // index into the signature registry, -1 = interpreted
     uint64_t out_elems;
     int32_t out_esize;
+    int32_t n_out;                        // > 1: tuple-typed root
+    int32_t out_esizes[MDIM_MAX_OUTS];
     Program prog;
     TransposePlan tr;
     FoldRowsPlan fr;

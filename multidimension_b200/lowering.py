@@ -205,10 +205,15 @@ class Emitted:
 
 
 def emit(root, axes, location):
-    """root: scalar Node; axes: the output's position axes in to_usize order;
-    location: 'device' | 'host' — which pointer of each storage object to write."""
+    """root: scalar Node, or a list of scalar Nodes — the scalar leaves of a tuple-typed element, written out under ONE
+    MDIM_NODE_TUPLE root so that a single kernel launch fills every leaf's run (structure of arrays, include/mdim.h);
+    axes: the output's position axes in to_usize order; location: 'device' | 'host' — which pointer of each storage to write."""
     order = []   # post-order, children before parents; shared subtrees are emitted per use
     red_axes = []
+    if isinstance(root, (list, tuple)):
+        if len(root) > F.MAX_OUTS:
+            raise Unsupported(f"a tuple-typed element with {len(root)} scalar leaves (> {F.MAX_OUTS}): collect the leaves separately")
+        root = Node(F.TUPLE, root[0].dtype, children=tuple(root))
 
     def visit(n):
         for c in n.children:
@@ -270,6 +275,8 @@ def emit(root, axes, location):
             d.imm.u64 = imm_bits(n.dtype, n.imm)
         if n.kind == F.FOLD and len(n.children) == 2:  # (init view, body): `let mut s = init.at(i)`
             d.n_comp = 2
+        if n.kind == F.TUPLE:
+            d.n_comp = len(n.children)
     e = F.Expr()
     e.abi_version = F.ABI_VERSION
     e.rank = len(axes)
@@ -281,4 +288,6 @@ def emit(root, axes, location):
     out_len = 1
     for a in axes:
         out_len *= a.length
-    return Emitted(e, arr, order, root.dtype, out_len, bufs)
+    em = Emitted(e, arr, order, root.dtype, out_len, bufs)
+    em.out_dtypes = [c.dtype for c in root.children] if root.kind == F.TUPLE else [root.dtype]
+    return em

@@ -98,6 +98,11 @@ class Context:
     def collect(self, expr, out_dptr, flags=0):
         self.check(self.lib.mdim_collect(self.handle, C.byref(expr), C.c_void_p(out_dptr), flags))
 
+    def collect_tuple(self, expr, out_dptrs, flags=0):
+        """mdim_collect_tuple: one launch fills the run of every scalar leaf of a tuple-typed element."""
+        outs = (C.c_void_p * len(out_dptrs))(*out_dptrs)
+        self.check(self.lib.mdim_collect_tuple(self.handle, C.byref(expr), outs, len(out_dptrs), flags))
+
     def collect_host(self, expr, out_hptr, flags=0):
         self.check(self.lib.mdim_collect_host(self.handle, C.byref(expr), C.c_void_p(out_hptr), flags))
 

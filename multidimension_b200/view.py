@@ -293,8 +293,12 @@ class View:
         leaves_T = _T_leaves(self.T)
         storages = []
         outs = list(out) if isinstance(out, (tuple, list)) else ([out] if out is not None else [None] * len(leaves_T))
-        for node, T, o in zip(L.flatten_value(value), leaves_T, outs):
-            storages.append(_run(ctx, node, axes, flags, location, o))
+        nodes = L.flatten_value(value)
+        if 1 < len(nodes) <= F.MAX_OUTS and all(_location_of(n, location) == "device" for n in nodes):
+            storages = _run_tuple(ctx, nodes, axes, flags, outs)  # ONE kernel launch: shared operands are read once
+        else:  # host-resident operands (mdim_collect_host is per leaf), or more leaves than one launch writes
+            for node, T, o in zip(nodes, leaves_T, outs):
+                storages.append(_run(ctx, node, axes, flags, location, o))
         st = _build_like(self.T, list(storages)) if isinstance(self.T, tuple) else storages[0]
         return Array(I_out, size_out, st, self.T)
 
@@ -438,6 +442,26 @@ def _location_of(node, requested):
     if requested:
         return requested
     return "host" if homes == {"host"} else "device"
+
+
+def _run_tuple(ctx, nodes, axes, flags, outs):
+    """Device-resident collect of a tuple-typed view: every scalar leaf's run from one launch (mdim_collect_tuple)."""
+    def visit(n):
+        for c in n.children:
+            visit(c)
+        if n.kind in (F.LEAF, F.GATHER) and n.buf is not None:
+            n.buf.ensure_device(ctx)
+    for n in nodes:
+        visit(n)
+    em = L.emit(list(nodes), axes, "device")
+    sts = []
+    for dt, o in zip(em.out_dtypes, outs):
+        st = o if o is not None else Storage.device(ctx, dt, em.out_len)
+        if st.n != em.out_len or st.dtype != dt:
+            raise Panic(F.ERR_SIZE, "output buffer does not match the view")
+        sts.append(st)
+    ctx.collect_tuple(em.expr, [s.dptr for s in sts], flags)
+    return sts
 
 
 def _run(ctx, node, axes, flags, location, out):

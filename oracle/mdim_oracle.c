@@ -54,6 +54,7 @@ static int arity(const mdim_node* n) {
         case MDIM_NODE_FOLD: return n->n_comp == 2 ? 2 : 1; /* (init view, body) or body alone */
         case MDIM_NODE_BINARY: case MDIM_NODE_CONCAT: return 2;
         case MDIM_NODE_GATHER: return n->n_comp;
+        case MDIM_NODE_TUPLE: return n->n_comp; /* root only: one output run per child (structure of arrays) */
     }
     return -1;
 }
@@ -377,6 +378,14 @@ static void each(oracle_t* o, int axis, sink_t* s) {
     if (o->failed) return;
     if (axis == o->e->rank) {
         int root = o->e->n_nodes - 1;
+        if (o->e->nodes[root].kind == MDIM_NODE_TUPLE) { /* a tuple-typed element: every scalar leaf goes to its own run */
+            for (int c = 0; c < o->n_child[root] && !o->failed; ++c) {
+                mdim_scalar v = at(o, o->child[root][c]);
+                if (!o->failed) push(&s[c], v);
+            }
+            if (!o->failed) o->position++;
+            return;
+        }
         mdim_scalar v = at(o, root);
         if (!o->failed) { push(s, v); o->position++; }
         return;
@@ -421,6 +430,26 @@ static int validate(oracle_t* o) {
     return sp == 1 ? MDIM_OK : MDIM_ERR_INVALID;
 }
 
+/* View::collect of a tuple-typed view (root = MDIM_NODE_TUPLE): one dense row-major run per scalar leaf (include/mdim.h). */
+int mdim_oracle_collect_tuple(const mdim_expr* e, void* const* outs, int n_outs, mdim_error_info* err) {
+    oracle_t* o = (oracle_t*)calloc(1, sizeof *o);
+    if (!o) return MDIM_ERR_NOMEM;
+    o->e = e; o->err = err;
+    if (err) memset(err, 0, sizeof *err);
+    int st = validate(o);
+    const mdim_node* root = &e->nodes[e->n_nodes - 1];
+    if (st == MDIM_OK && (root->kind != MDIM_NODE_TUPLE || root->n_comp != n_outs || n_outs > MDIM_MAX_OUTS)) st = MDIM_ERR_INVALID;
+    if (st != MDIM_OK) { free(o); if (err) err->status = st; return st; }
+    uint64_t len = 1;
+    for (int a = 0; a < e->rank; ++a) len *= e->length[a];
+    sink_t s[MDIM_MAX_OUTS];
+    for (int c = 0; c < n_outs; ++c) { s[c].items = outs[c]; s[c].len = 0; s[c].cap = len; s[c].dtype = e->nodes[o->child[e->n_nodes - 1][c]].dtype; }
+    each(o, 0, s);
+    if (o->failed) { st = (err && err->status) ? err->status : MDIM_ERR_INVALID; free(o); return st; }
+    free(o);
+    return MDIM_OK;
+}
+
 /* View::collect (src/view.rs:146-150) into a dense row-major host buffer. */
 int mdim_oracle_collect(const mdim_expr* e, void* out, mdim_error_info* err) {
     oracle_t* o = (oracle_t*)calloc(1, sizeof *o);
@@ -428,6 +457,7 @@ int mdim_oracle_collect(const mdim_expr* e, void* out, mdim_error_info* err) {
     o->e = e; o->err = err;
     if (err) memset(err, 0, sizeof *err);
     int st = validate(o);
+    if (st == MDIM_OK && e->nodes[e->n_nodes - 1].kind == MDIM_NODE_TUPLE) st = MDIM_ERR_INVALID; /* needs mdim_oracle_collect_tuple */
     if (st != MDIM_OK) { free(o); if (err) err->status = st; return st; }
     uint64_t len = 1;
     for (int a = 0; a < e->rank; ++a) len *= e->length[a]; /* I::length, src/index.rs:104-107 */

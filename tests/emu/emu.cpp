@@ -55,6 +55,17 @@ static int run(const Plan& p, const Program& P, void* out, ErrWord* err, uint64_
 }
 }  // namespace mdim
 
+static void* const* g_more_outs = nullptr;  // set by mdim_emu_collect_tuple for the duration of one call
+
+extern "C" int mdim_emu_collect(const mdim_expr* e, void* out, uint32_t flags, mdim_error_info* info, char* describe, size_t describe_len);
+extern "C" int mdim_emu_collect_tuple(const mdim_expr* e, void* const* outs, int n_outs, uint32_t flags, mdim_error_info* info, char* describe, size_t describe_len) {
+    g_more_outs = outs;
+    const int st = mdim_emu_collect(e, outs[0], flags, info, describe, describe_len);
+    g_more_outs = nullptr;
+    (void)n_outs;
+    return st;
+}
+
 extern "C" int mdim_emu_collect(const mdim_expr* e, void* out, uint32_t flags, mdim_error_info* info, char* describe, size_t describe_len) {
     using namespace mdim;
     Plan* plan = new Plan();
@@ -64,6 +75,10 @@ extern "C" int mdim_emu_collect(const mdim_expr* e, void* out, uint32_t flags, m
     if (describe && describe_len) snprintf(describe, describe_len, "%s", st ? why : plan->describe);
     if (st) { if (info) { info->status = st; snprintf(info->message, sizeof info->message, "%s", why); } delete plan; return st; }
     if (plan->kind == KK_EMPTY) { delete plan; return MDIM_OK; }
+    if (plan->n_out > 1) {
+        if (!g_more_outs) { delete plan; return MDIM_ERR_INVALID; }
+        for (int k = 1; k < plan->n_out; ++k) plan->prog.out_more[k - 1] = g_more_outs[k];
+    }
     ErrWord err;
     memset(&err, 0, sizeof err);
     err.pos = ~0ull;

@@ -58,6 +58,38 @@ class CheckerPanic(Exception):
         self.status, self.info = status, info
 
 
+def _run_host_tuple(view, runner):
+    """A tuple-typed view through ONE descriptor with an MDIM_NODE_TUPLE root: runner(em, [out arrays], info)."""
+    groups, value = view._lower()
+    em = L.emit(list(L.flatten_value(value)), _flat(groups), "host")
+    outs = [np.zeros(em.out_len, dtype=NP_OF[dt]) for dt in em.out_dtypes]
+    info = F.ErrorInfo()
+    st = runner(em, outs, info)
+    if st != F.OK:
+        raise CheckerPanic(st, info)
+    return outs
+
+
+def oracle_collect_tuple(view):
+    lib = oracle_lib()
+    lib.mdim_oracle_collect_tuple.restype = C.c_int
+
+    def run(em, outs, info):
+        ptrs = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
+        return lib.mdim_oracle_collect_tuple(C.byref(em.expr), ptrs, len(outs), C.byref(info))
+    return _shape_result(view, _run_host_tuple(view, run))
+
+
+def emu_collect_tuple(view, flags=0):
+    lib = emu_lib()
+    lib.mdim_emu_collect_tuple.restype = C.c_int
+
+    def run(em, outs, info):
+        ptrs = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
+        return lib.mdim_emu_collect_tuple(C.byref(em.expr), ptrs, len(outs), C.c_uint32(flags), C.byref(info), None, C.c_size_t(0))
+    return _shape_result(view, _run_host_tuple(view, run))
+
+
 def _run_host(view, runner):
     groups, value = view._lower()
     axes = _flat(groups)

@@ -31,7 +31,8 @@ from multidimension_b200 import _ffi as F
 from multidimension_b200 import sharding
 from oracle import reference_model as M
 
-from helpers import emu_collect, assert_same_bits, CheckerPanic
+from helpers import emu_collect, emu_collect_tuple, assert_same_bits, CheckerPanic
+from multidimension_b200 import lowering as L
 
 MAX_ELEMS = 6000      # per collected view (the model is pure Python)
 MAX_AXES = 8          # MDIM_MAX_RANK
@@ -50,6 +51,8 @@ def backend(request):
 
 def product_collect(view, backend):
     if backend == "emu":
+        if isinstance(view.T, tuple) and len(L.flatten_value(view._lower()[1])) <= F.MAX_OUTS:
+            return emu_collect_tuple(view)  # tuple-typed elements: ONE descriptor with an MDIM_NODE_TUPLE root, as on the GPU
         return emu_collect(view)
     return view.collect(location="device", ctx=_gpu_ctx[0]).as_ref()
 
