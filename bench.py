@@ -846,6 +846,23 @@ def bench_scaling_ops(B, ta, tout):
         row("c4_fold_sharded_axis_peer_mapped_bit_exact", alg0, ms, n1_ms, exact.describe(), nvlink_in_bytes=4 * n4 // world * (world - 1) // world,
             note="every rank folds ITS block of the result over all ranks' rows in index order, reading the peers over NVLink: bit-identical to the reference")
 
+    if world > 1:
+        # the same bit-exact fold as ONE fused kernel per GPU: the running values travel rank to rank over NVLink, pipelined
+        # over column slices (csrc/k_fold_ring.cu); the result lands on EVERY rank
+        tring = torch.empty(J * K, device="cuda", dtype=torch.float32)
+        sring = out_storage(tring, F.F32)
+        blk_rows = out_storage(t4[rank * ib * J * K:(rank + 1) * ib * J * K], F.F32)
+
+        def ring():
+            comm.fold_sharded_axis(blk_rows, ib, J * K, P.Add, np.float32(0), out=sring)
+        ring(); ctx.sync(); comm.fold_status()
+        assert torch.equal(tring, tfull), "pipelined ring fold over the sharded axis is not bit-exact"
+        ms, _ = time_launches(ring, steps, 3)
+        comm.fold_status()
+        row("c4_fold_sharded_axis_ring_pipelined_bit_exact", alg0, ms, n1_ms, "k_fold_ring (mdim_fold_sharded_axis)", nvlink_in_bytes=4 * J * K,
+            note="ONE fused kernel per GPU: rank r continues rank r-1's running values slice by slice (TMA row tiles, flags in peer memory); "
+                 "bit-identical to the reference's sequential chain, replicated result, no NCCL call")
+
     # ---- C5: the rank-5 chain, 2^30 outputs cut into N blocks of the outermost index -------------------------------------------------
     Pn = Qn = Rn = 64
     g5 = torch.Generator(device="cuda")
