@@ -53,6 +53,47 @@ __device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch) 
     return false;
 }
 
+// One staged tile folded into the running values, strictly in row order: this IS the reference's add chain.  The element type
+// and operator are compile-time here (bin_op's switches fold away): dispatched once per tile, not once per element.
+template <class S, int DT, int OP>
+__device__ __forceinline__ void fold_tile(S (&acc)[4], uint32_t p, uint32_t rows) {
+    constexpr int ES = (int)sizeof(S), SC = kRingCons * 4;
+#pragma unroll 8
+    for (uint32_t r = 0; r < rows; ++r) {
+        S x[4];
+        if constexpr (ES == 4) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(p + r * SC * ES));
+        else {
+            asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x[0]), "=l"(x[1]) : "r"(p + r * SC * ES));
+            asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x[2]), "=l"(x[3]) : "r"(p + r * SC * ES + 16));
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { bool arith = false; acc[e] = bin_op<S>(DT, OP, DT, acc[e], x[e], arith); }
+    }
+}
+template <class S, int DT>
+__device__ __forceinline__ void fold_tile_op(int op, S (&acc)[4], uint32_t p, uint32_t rows) {
+    switch (op) {
+        case MDIM_ADD: fold_tile<S, DT, MDIM_ADD>(acc, p, rows); break;
+        case MDIM_SUB: fold_tile<S, DT, MDIM_SUB>(acc, p, rows); break;
+        case MDIM_MUL: fold_tile<S, DT, MDIM_MUL>(acc, p, rows); break;
+        case MDIM_AND: fold_tile<S, DT, MDIM_AND>(acc, p, rows); break;
+        case MDIM_OR: fold_tile<S, DT, MDIM_OR>(acc, p, rows); break;
+        default: fold_tile<S, DT, MDIM_XOR>(acc, p, rows); break;
+    }
+}
+template <class S>
+__device__ __forceinline__ void fold_tile_dispatch(int dtype, int op, S (&acc)[4], uint32_t p, uint32_t rows) {
+    if constexpr (sizeof(S) == 4) {
+        if (dtype == MDIM_F32) fold_tile_op<S, MDIM_F32>(op, acc, p, rows);
+        else if (dtype == MDIM_I32) fold_tile_op<S, MDIM_I32>(op, acc, p, rows);
+        else fold_tile_op<S, MDIM_U32>(op, acc, p, rows);
+    } else {
+        if (dtype == MDIM_F64) fold_tile_op<S, MDIM_F64>(op, acc, p, rows);
+        else if (dtype == MDIM_I64) fold_tile_op<S, MDIM_I64>(op, acc, p, rows);
+        else fold_tile_op<S, MDIM_U64>(op, acc, p, rows);
+    }
+}
+
 template <class S>  // S = uint32_t (4-byte elements) or uint64_t (8-byte)
 __global__ void __launch_bounds__(kRingThreads) k_fold_ring(const __grid_constant__ CUtensorMap rows_map, const __grid_constant__ FoldRingArgs A) {
     constexpr int ES = (int)sizeof(S), EPT = 4;            // elements per consumer thread
@@ -123,17 +164,7 @@ __global__ void __launch_bounds__(kRingThreads) k_fold_ring(const __grid_constan
                 mbar_wait_parity(bars + 16 * st, (drain / kRingStages) & 1);
                 const uint32_t rows = min((uint64_t)ROWS, A.n_rows - (uint64_t)t * ROWS);
                 const uint32_t p = base + st * kRingStageBytes + (uint32_t)ct * EPT * ES;
-#pragma unroll 4
-                for (uint32_t r = 0; r < rows; ++r) {  // strictly in index order: this IS the reference's add chain
-                    S x[EPT];
-                    if constexpr (ES == 4) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(p + r * SC * ES));
-                    else {
-                        asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x[0]), "=l"(x[1]) : "r"(p + r * SC * ES));
-                        asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x[2]), "=l"(x[3]) : "r"(p + r * SC * ES + 16));
-                    }
-#pragma unroll
-                    for (int e = 0; e < EPT; ++e) { bool arith = false; acc[e] = bin_op<S>(A.dtype, A.op, A.dtype, acc[e], x[e], arith); }
-                }
+                fold_tile_dispatch<S>(A.dtype, A.op, acc, p, rows);
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 16 * st + 8) : "memory");
             }
             // hand the running values on (or, on the last rank, publish the result to everyone)
