@@ -853,8 +853,7 @@ def bench_scaling_ops(B, ta, tout):
         sring = out_storage(tring, F.F32)
         blk_rows = out_storage(t4[rank * ib * J * K:(rank + 1) * ib * J * K], F.F32)
 
-        def ring():
-            comm.fold_sharded_axis(blk_rows, ib, J * K, P.Add, np.float32(0), out=sring)
+        ring, _ = comm.prepare_fold_sharded_axis(blk_rows, ib, J * K, P.Add, np.float32(0), out=sring)
         ring(); ctx.sync(); comm.fold_status()
         assert torch.equal(tring, tfull), "pipelined ring fold over the sharded axis is not bit-exact"
         ms, _ = time_launches(ring, steps, 3)

@@ -32,10 +32,12 @@ namespace mdim {
 
 namespace {
 
-constexpr int kRingThreads = 96;        // warp 0: producer (one lane) and flag poller; warps 1-2: consumers
+constexpr int kRingThreads = 128;       // warp 0: producer (one lane); warps 1-2: consumers; warp 3: publisher (fences and flags, off the adders' path)
 constexpr int kRingCons = 64;
 constexpr int kRingStageBytes = 32 * 1024;
 constexpr int kRingStages = 6;
+constexpr int kRingMaxLocalSlices = 64;  // slices one CTA may own: each has its OWN publish barrier (used once per launch, so the
+                                         // adders can run any number of slices ahead of the publisher without overrunning a phase)
 constexpr unsigned long long kSpinLimit = 40ull * 1000 * 1000;  // polls of a local flag (~50 ns each): ~2 s
 
 __device__ __forceinline__ uint32_t rsm(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -48,7 +50,7 @@ __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) 
 __device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch) {
     for (unsigned long long spins = 0; spins < kSpinLimit; ++spins) {
         if ((int32_t)(ld_acquire_sys(flag) - epoch) >= 0) return true;
-        __nanosleep(40);
+        if (spins > 16) __nanosleep(40);
     }
     return false;
 }
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(kRingThreads) k_fold_ring(const __grid_constan
     extern __shared__ uint8_t ring_raw[];
     const uint32_t base = (rsm(ring_raw) + 127u) & ~127u;
     const uint32_t bars = base + kRingStages * kRingStageBytes;  // full[s] at bars + 16 s, empty[s] at bars + 16 s + 8
+    const uint32_t pub_bars = bars + 16 * kRingStages;           // publish[i] for the i-th slice of this CTA: 64 consumer arrivals
     __shared__ int timed_out;
     const int tid = threadIdx.x, warp = tid >> 5;
     pdl_entry(false);  // reads the caller's rows: always waits for its predecessor in the stream
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(kRingThreads) k_fold_ring(const __grid_constan
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 16 * s) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 16 * s + 8), "r"(kRingCons) : "memory");
         }
+        for (int i = 0; i < kRingMaxLocalSlices; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pub_bars + 8 * i), "r"(kRingCons) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -138,19 +142,34 @@ __global__ void __launch_bounds__(kRingThreads) k_fold_ring(const __grid_constan
         producer_done:
             if (*(volatile int*)&timed_out) __nanosleep(200000);  // let the loads still in flight land before the CTA gives its shared memory back
         }
+    } else if (warp == 3) {  // ---- publisher: once the consumers have stored a slice's values, make them visible and raise the flag(s)
+        const bool last = A.rank == A.world - 1;
+        uint32_t i = 0;
+        for (uint64_t s = blockIdx.x; s < n_slices; s += gridDim.x, ++i) {
+            if (tid != 96) continue;
+            mbar_wait_parity(pub_bars + 8 * i, 0);  // all 64 consumers have stored slice i's values (or given up)
+            if (!*(volatile int*)&timed_out) {
+                // the consumers' stores happen before their arrival, the arrival before this fence: ONE system-scope fence by ONE
+                // thread publishes the whole slice (fence + relaxed store = release); the adders never wait for it
+                __threadfence_system();
+                if (last) { for (int d = 0; d < A.world; ++d) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(A.flag_final[d] + s), "r"(A.epoch) : "memory"); }
+                else asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(A.next_flag_in + s), "r"(A.epoch) : "memory");
+            }
+        }
     } else {  // ---- consumers: 64 threads, EPT consecutive columns each -----------------------------------------------------
         const int ct = tid - 32;
         const bool first = A.rank == 0, last = A.rank == A.world - 1;
-        for (uint64_t s = blockIdx.x; s < n_slices; s += gridDim.x) {
+        uint32_t li = 0;  // index of the slice among this CTA's
+        for (uint64_t s = blockIdx.x; s < n_slices; s += gridDim.x, ++li) {
             const uint64_t col = s * SC + (uint64_t)ct * EPT;
             S acc[EPT];
             if (first) {
 #pragma unroll
                 for (int e = 0; e < EPT; ++e) acc[e] = (S)A.init;
             } else {
-                if (ct == 0 && !wait_flag(A.flag_in + s, A.epoch)) timed_out = 1;
+                if (ct == 0 && !timed_out && !wait_flag(A.flag_in + s, A.epoch)) timed_out = 1;
                 asm volatile("bar.sync 1, %0;" ::"n"(kRingCons) : "memory");  // consumers only
-                if (timed_out) break;
+                if (timed_out) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pub_bars + 8 * li) : "memory"); continue; }  // the publisher must not wait forever
 #pragma unroll
                 for (int e = 0; e < EPT; ++e) {  // written by the previous rank over NVLink: bypass L1
                     if (col + e < A.n_cols) {
@@ -174,25 +193,26 @@ __global__ void __launch_bounds__(kRingThreads) k_fold_ring(const __grid_constan
 #pragma unroll
                 for (int e = 0; e < EPT; ++e) if (col + e < A.n_cols) dst[e] = acc[e];
             }
-            __threadfence_system();
-            asm volatile("bar.sync 1, %0;" ::"n"(kRingCons) : "memory");
-            if (ct == 0) {
-                if (last) { for (int d = 0; d < A.world; ++d) st_release_sys(A.flag_final[d] + s, A.epoch); }
-                else st_release_sys(A.next_flag_in + s, A.epoch);
-            }
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pub_bars + 8 * li) : "memory");  // hand the slice to the publisher and move on
         }
     }
     __syncthreads();
-    // ---- every slice of this CTA: wait for the finished values, copy them from the local result area to `out` -------------
-    for (uint64_t s = blockIdx.x; s < n_slices && !timed_out; s += gridDim.x) {
-        if (tid == 0 && !wait_flag(A.flag_final[A.rank] + s, A.epoch)) timed_out = 1;
-        __syncthreads();
-        if (timed_out) break;
-        for (uint64_t c = s * SC + tid; c < min((s + 1) * (uint64_t)SC, A.n_cols); c += kRingThreads) {
-            S v;
-            if constexpr (ES == 4) asm volatile("ld.global.cv.u32 %0, [%1];" : "=r"(v) : "l"((const S*)A.result[A.rank] + c));
-            else asm volatile("ld.global.cv.u64 %0, [%1];" : "=l"(v) : "l"((const S*)A.result[A.rank] + c));
-            ((S*)A.out)[c] = v;
+    // ---- every slice of this CTA: wait for the finished values (thread i polls the i-th slice's flag), then ONE parallel
+    //      pass copies them from the local result area to `out` ------------------------------------------------------------
+    const uint32_t my_slices = blockIdx.x < n_slices ? (uint32_t)((n_slices - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    for (uint32_t i = tid; i < my_slices && !timed_out; i += kRingThreads)
+        if (!wait_flag(A.flag_final[A.rank] + (blockIdx.x + (uint64_t)i * gridDim.x), A.epoch)) timed_out = 1;
+    __syncthreads();
+    if (!timed_out) {
+        const uint32_t total = my_slices * SC;
+        for (uint32_t k = tid; k < total; k += kRingThreads) {
+            const uint64_t c = (blockIdx.x + (uint64_t)(k / SC) * gridDim.x) * SC + (k % SC);
+            if (c < A.n_cols) {
+                S v;
+                if constexpr (ES == 4) asm volatile("ld.global.cv.u32 %0, [%1];" : "=r"(v) : "l"((const S*)A.result[A.rank] + c));
+                else asm volatile("ld.global.cv.u64 %0, [%1];" : "=l"(v) : "l"((const S*)A.result[A.rank] + c));
+                ((S*)A.out)[c] = v;
+            }
         }
     }
     if (timed_out && tid == 0) atomicExch(A.error, 1u);
@@ -223,9 +243,10 @@ int launch_fold_ring(const FoldRingArgs& A, const void* rows, int sm_count, cuda
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return -1;
     } else if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(rows), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return -1;
-    const size_t smem = (size_t)kRingStages * kRingStageBytes + 16 * kRingStages + 256;
+    const size_t smem = (size_t)kRingStages * kRingStageBytes + 16 * kRingStages + 8 * kRingMaxLocalSlices + 256;
     const uint64_t n_slices = (A.n_cols + kRingCons * 4 - 1) / (kRingCons * 4);
     const int grid = (int)std::min<uint64_t>(n_slices, (uint64_t)sm_count);  // one CTA per SM: every CTA is resident, so waiting on peers cannot starve anyone
+    if ((n_slices + grid - 1) / grid > (uint64_t)kRingMaxLocalSlices) return -1;
     cudaError_t e;
     if (es == 4) {
         static const bool ok = cudaFuncSetAttribute(k_fold_ring<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;

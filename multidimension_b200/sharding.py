@@ -193,6 +193,25 @@ class Comm:
                                                            C.c_void_p(out.dptr)))
         return out
 
+    def prepare_fold_sharded_axis(self, local_rows, n_rows_local, n_cols, op, init, out=None):
+        """The same call with its arguments bound once: -> (run, out Storage); `run()` is a single C-ABI call (a 30 us kernel
+        must not wait for Python to rebuild its arguments)."""
+        import ctypes as C
+        from . import lowering as L
+        if local_rows.n != n_rows_local * n_cols:
+            raise F.Panic(F.ERR_SIZE, "fold_sharded_axis: the block must hold n_rows_local x n_cols elements")
+        out = out or Storage.device(self.ctx, local_rows.dtype, n_cols)
+        imm = F.Scalar()
+        imm.u64 = L.imm_bits(local_rows.dtype, init)
+        fn, check = self.ctx.lib.mdim_fold_sharded_axis, self.ctx.check
+        args = (self.ctx.handle, C.c_void_p(local_rows.dptr), C.c_uint64(n_rows_local), C.c_uint64(n_cols), C.c_int(local_rows.dtype), C.c_int(op.code), imm, C.c_void_p(out.dptr))
+
+        def run():
+            st = fn(*args)
+            if st != F.OK:
+                check(st)
+        return run, out
+
     def fold_status(self):
         self.ctx.check(self.ctx.lib.mdim_fold_sharded_axis_status(self.ctx.handle))
 

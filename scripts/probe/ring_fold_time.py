@@ -27,7 +27,8 @@ for rows in (1024, 512, 128):
     ev = fold_rows(a.transpose((), usize, usize, ()).iso((usize, usize)), usize, usize, Add, np.float32(0))
     ref = torch.empty(C_, device="cuda", dtype=torch.float32)
     pe = ev.prepare(out=Storage.wrap_device(ctx, F.F32, C_, ref.data_ptr(), keep=ref), flags=F.COLLECT_ASYNC)
-    for name, fn in (("k_fold_ring", lambda: comm.fold_sharded_axis(st, rows, C_, Add, np.float32(0), out=so)), ("evaluator", pe.run)):
+    ring_run, _ = comm.prepare_fold_sharded_axis(st, rows, C_, Add, np.float32(0), out=so)
+    for name, fn in (("k_fold_ring", ring_run), ("evaluator", pe.run)):
         for _ in range(3):
             fn()
         ctx.sync()
