@@ -256,21 +256,26 @@ def all_reduce_partial(partial_storage, op, comm):
     return partial_storage
 
 
-# Measured on one 8 x B200 NVSwitch box (profiles/r1_bench_n*_multi_ops.json, profiles/r2_scale_*.json):
-_REMOTE_GATHERS_PER_S = 8.0e9    # uniform-random 4-byte reads of a peer's HBM over NVLink, per GPU (2 GPUs: 7.0e9, 8 GPUs: 1.1e10)
-_LOCAL_GATHERS_PER_S = 44.0e9    # the same reads from the GPU's own HBM (config 3: 2^28 in 6.0 ms)
-_ALLGATHER_IN_BYTES_PER_S = 600.0e9  # NCCL all-gather, bytes arriving per GPU per second (615e9 at 8 GPUs)
+# Measured on one 8 x B200 NVSwitch box (profiles/r2_bench_n{2,4,8}.json, `scaling_ops`), per number of GPUs:
+_REMOTE_GATHERS_PER_S = {2: 8.3e9, 4: 7.3e9, 8: 1.1e10}   # uniform-random 4-byte reads of the peers' HBM over NVLink, per GPU
+_LOCAL_GATHERS_PER_S = 44.0e9                              # the same reads from the GPU's own HBM (config 3: 2^28 in 6.0 ms)
+_ALLGATHER_IN_BYTES_PER_S = {2: 480.0e9, 4: 620.0e9, 8: 637.0e9}  # mdim_allgather (NCCL), bytes arriving per GPU per second
+
+
+def _rate(table, world):
+    return table[min(table, key=lambda n: abs(n - world))]
 
 
 def choose_compose_route(n_idx_local, src_bytes, world, reuse=1):
     """How should `idx.compose(src)` run when `src` is sharded over `world` GPUs and this rank holds `n_idx_local`
     indices?  -> "peer" (the gather kernel reads every element from the GPU that owns it, mdim_node.peer[]) or
-    "allgather" (mdim_allgather the source first, then gather locally).  A cost model over the three measured rates
+    "allgather" (mdim_allgather the source first, then gather locally).  A cost model over the measured rates
     above; `reuse` = how many collects will read the gathered source (the all-gather is paid once).
-    Measured crossover: all-gather first wins at 2 GPUs (7.5 vs 9.6 ms), peer-mapped from 4 GPUs up (8 GPUs: 2.7 vs 6.6 ms)."""
+    Measured crossover (2^28 indices into a 4 GiB source): all-gather first wins at 2 GPUs (7.4 vs 9.7 ms) and at 4 (6.7 vs 7.3),
+    peer-mapped at 8 (2.7 vs 6.6 ms)."""
     if world <= 1:
         return "local"
     remote = n_idx_local * (world - 1) / world
-    t_peer = remote / _REMOTE_GATHERS_PER_S + (n_idx_local - remote) / _LOCAL_GATHERS_PER_S
-    t_ag = src_bytes * (world - 1) / world / _ALLGATHER_IN_BYTES_PER_S / max(reuse, 1) + n_idx_local / _LOCAL_GATHERS_PER_S
+    t_peer = remote / _rate(_REMOTE_GATHERS_PER_S, world) + (n_idx_local - remote) / _LOCAL_GATHERS_PER_S
+    t_ag = src_bytes * (world - 1) / world / _rate(_ALLGATHER_IN_BYTES_PER_S, world) / max(reuse, 1) + n_idx_local / _LOCAL_GATHERS_PER_S
     return "peer" if t_peer <= t_ag else "allgather"
