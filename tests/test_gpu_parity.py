@@ -423,3 +423,40 @@ def test_shape_specialised_kernels_on_first_use():
                         "(rank5 or mixed_strides or concat or diagonal_guards or transpose_batched or fold_over_outermost or two_components) and gpu"],
                        env=env, capture_output=True, text=True, cwd=root)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_dependency_aware_launches_respect_raw_war_and_waw_hazards():
+    """csrc/launch.cuh: a collect whose buffers are untouched by the kernels still in flight skips the stream-order wait.
+    Chains with read-after-write, write-after-read and write-after-write hazards between back-to-back ASYNC launches must
+    still give the sequential result (and independent launches in between must not break the chain)."""
+    from multidimension_b200.runtime import Storage
+    c = P.Context(0)
+    rng = np.random.default_rng(12)
+    n = 1024
+    x0 = rng.uniform(-1, 1, n * n).astype(np.float32)
+    bufs = [Storage.device(c, F.F32, n * n) for _ in range(4)]
+    c.upload(bufs[0].dptr, x0)
+    other_src = [Array.new((usize, usize), (n, n), rng.uniform(-1, 1, n * n).astype(np.float32)).to_device(c) for _ in range(3)]
+    other_out = [Storage.device(c, F.F32, n * n) for _ in range(3)]
+
+    def arr(k):
+        return Array((usize, usize), (n, n), bufs[k], "f32")
+    for rounds in range(20):
+        # RAW chain: b1 = t(b0); b2 = t(b1) (= b0); b3 = b2 * b1' ... interleaved with independent transposes
+        arr(0).transpose((), usize, usize, ()).collect(out=bufs[1], ctx=c, flags=F.COLLECT_ASYNC)
+        other_src[0].transpose((), usize, usize, ()).collect(out=other_out[0], ctx=c, flags=F.COLLECT_ASYNC)       # independent
+        arr(1).transpose((), usize, usize, ()).collect(out=bufs[2], ctx=c, flags=F.COLLECT_ASYNC)                     # RAW on b1
+        other_src[1].transpose((), usize, usize, ()).collect(out=other_out[1], ctx=c, flags=F.COLLECT_ASYNC)       # independent
+        (arr(2) * arr(1) + Scalar(1.0, "f32")).collect(out=bufs[3], ctx=c, flags=F.COLLECT_ASYNC)                   # RAW on b2, b1
+        other_src[2].transpose((), usize, usize, ()).collect(out=bufs[1], ctx=c, flags=F.COLLECT_ASYNC)              # WAR on b1 (b3's kernel reads it), WAW on b1
+        arr(3).transpose((), usize, usize, ()).collect(out=bufs[2], ctx=c, flags=F.COLLECT_ASYNC)                     # WAW on b2, RAW on b3
+    c.sync()
+    X = x0.reshape(n, n)
+    want3 = (X * X.T + np.float32(1)).astype(np.float32)
+    assert np.array_equal(bufs[3].to_numpy().reshape(n, n), want3)
+    assert np.array_equal(bufs[2].to_numpy().reshape(n, n), want3.T)
+    assert np.array_equal(bufs[1].to_numpy().reshape(n, n), other_src[2].as_ref().reshape(n, n).T)
+    for k in range(2):
+        assert np.array_equal(other_out[k].to_numpy().reshape(n, n), other_src[k].as_ref().reshape(n, n).T)
+    c.close()
