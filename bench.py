@@ -862,6 +862,27 @@ def bench_scaling_ops(B, ta, tout):
             note="ONE fused kernel per GPU: rank r continues rank r-1's running values slice by slice (TMA row tiles, flags in peer memory); "
                  "bit-identical to the reference's sequential chain, replicated result, no NCCL call")
 
+    if world > 1:
+        # the all-reduce route as ONE fused kernel per GPU (csrc/k_fold_xchg.cu): sequential per-rank partial folds, combined in
+        # RANK ORDER inside the kernel from flag-in-data packets in peer memory — deterministic, checked bit for bit against that order
+        tblk = torch.empty(J * K, device="cuda", dtype=torch.float32)
+        blocked, _ = comm.prepare_fold_sharded_axis(blk_rows, ib, J * K, P.Add, np.float32(0), out=out_storage(tblk, F.F32), blocked=True)
+        blocked(); ctx.sync(); comm.fold_status()
+        want_blk = None
+        for r in range(world):
+            pr = torch.full((J * K,), 0.0 if r == 0 else -0.0, device="cuda", dtype=torch.float32)
+            for i in range(r * ib, (r + 1) * ib):
+                pr = pr + t4.view(I, J * K)[i]
+            want_blk = pr if r == 0 else want_blk + pr
+        assert torch.equal(tblk.view(torch.int32), want_blk.view(torch.int32)), "blocked fold over the sharded axis differs from the rank-ordered combination"
+        diff_b = (tblk.double() - tfull.double()).abs() / tfull.double().abs()
+        ms, _ = time_launches(blocked, steps, 3)
+        comm.fold_status()
+        row("c4_fold_sharded_axis_blocked_in_kernel_allreduce", alg0, ms, n1_ms, "k_fold_xchg (mdim_fold_sharded_axis_blocked)", nvlink_in_bytes=8 * J * K * (world - 1),
+            max_rel_diff_vs_reference_order=diff_b.max().item(), fraction_of_outputs_beyond_1e_6=(diff_b > 1e-6).double().mean().item(),
+            note="ONE fused kernel per GPU: sequential per-rank partial folds + an all-reduce in rank order inside the kernel (16-byte "
+                 "flag-in-data packets into peer HBM, no fence, no NCCL call); reassociated at the rank boundaries only, deterministic")
+
     # ---- C5: the rank-5 chain, 2^30 outputs cut into N blocks of the outermost index -------------------------------------------------
     Pn = Qn = Rn = 64
     g5 = torch.Generator(device="cuda")

@@ -283,6 +283,14 @@ int mdim_peer_table_close(mdim_ctx* ctx);                                       
 int mdim_fold_sharded_axis(mdim_ctx* ctx, const void* local_rows, uint64_t n_rows_local, uint64_t n_cols, int dtype, int op, mdim_scalar init,
                            void* out_device);
 int mdim_fold_sharded_axis_status(mdim_ctx* ctx);
+/* The all-reduce route of the same fold as ONE fused kernel per GPU (csrc/k_fold_xchg.cu), no NCCL call:
+ * P_r = rank r's rows folded sequentially (rank 0 starts from `init`, the others from the operator's identity: 0, 1, all-ones, and
+ * -0.0 for a float sum); out[c] = ((P_0 (op) P_1) (op) P_2) ... (op) P_{N-1} on EVERY rank, combined in rank order inside the kernel
+ * from flag-in-data packets written into peer-mapped HBM.  Bit-identical to the reference for integer and bitwise folds; a float
+ * fold is reassociated at the rank boundaries only (1e-6 relative) and is deterministic.  op: MDIM_ADD, MUL, AND, OR, XOR; 4- and
+ * 8-byte dtypes; rows and out 16-byte aligned, row length a multiple of 16 bytes.  Asynchronous; errors as above. */
+int mdim_fold_sharded_axis_blocked(mdim_ctx* ctx, const void* local_rows, uint64_t n_rows_local, uint64_t n_cols, int dtype, int op,
+                                   mdim_scalar init, void* out_device);
 
 /* Run-time specialisation (NVRTC) of `e`'s op tree, compile step only: needs no GPU.  0 = compiles for
  * sm_100a; MDIM_ERR_UNSUPPORTED = NVRTC not installed or the plan has a pre-built kernel; `log` gets details. */

@@ -104,6 +104,7 @@ SYMBOLS = [
     ("mdim_peer_table_close", C.c_int, [_P]),
     ("mdim_fold_sharded_axis", C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_int, C.c_int, Scalar, _P]),
     ("mdim_fold_sharded_axis_status", C.c_int, [_P]),
+    ("mdim_fold_sharded_axis_blocked", C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_int, C.c_int, Scalar, _P]),
     ("mdim_jit_check_nodevice", C.c_int, [C.POINTER(Expr), C.c_uint32, C.c_char_p, C.c_size_t]),
     ("mdim_abi_version", C.c_int, []),
 ]

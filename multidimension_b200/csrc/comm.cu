@@ -86,15 +86,19 @@ struct Comm {
     struct Opened { cudaIpcMemHandle_t handle; void* base; };  // one mapping per peer ALLOCATION, however many blocks live in it
     std::vector<Opened> opened;  // IPC mappings made by mdim_peer_table, closed by mdim_peer_table_close / shutdown
     // state of the pipelined fold over the sharded axis (k_fold_ring.cu): one allocation per rank, mapped into every rank
-    //   [inbox: kRingCap x 8 B][result: kRingCap x 8 B][flag_in: kRingSlices x 4 B][flag_final: kRingSlices x 4 B][error: 4 B]
+    //   [inbox: kRingCap x 16 B][result: kRingCap x 16 B][error: 4 B]   (flag-in-data lines: 2 x the data bytes)
     char* ring = nullptr;
     void* ring_peer[MDIM_MAX_PEERS] = {nullptr};
     uint32_t ring_epoch = 0;
+    // packet areas of the in-kernel all-reduce (k_fold_xchg.cu): [slot 0/1][source rank 0..N-1, results][kXchgCapWords x 8 B] + an error word
+    char* xchg = nullptr;
+    void* xchg_peer[MDIM_MAX_PEERS] = {nullptr};
+    uint32_t xchg_epoch = 0;
 };
+constexpr uint64_t kXchgCapWords = 1ull << 20;     // 32-bit words of columns per launch (4 MiB of a row; wider rows take several launches)
+inline size_t xchg_error_off(int world) { return (size_t)2 * (size_t)(world + 1) * kXchgCapWords * 8; }
 constexpr uint64_t kRingCap = 1ull << 20;          // columns per launch (a wider result is folded in several launches)
-constexpr uint64_t kRingSlices = kRingCap / 256;   // 256 columns per slice (k_fold_ring.cu)
-constexpr size_t kRingInboxOff = 0, kRingResultOff = kRingCap * 8, kRingFlagInOff = 2 * kRingCap * 8, kRingFlagFinalOff = kRingFlagInOff + kRingSlices * 4,
-                 kRingErrorOff = kRingFlagFinalOff + kRingSlices * 4, kRingBytes = kRingErrorOff + 256;
+constexpr size_t kRingInboxOff = 0, kRingResultOff = kRingCap * 16, kRingErrorOff = 2 * kRingCap * 16, kRingBytes = kRingErrorOff + 256;
 
 void comm_destroy(mdim_ctx* ctx) {
     Comm* c = ctx->comm;
@@ -102,6 +106,7 @@ void comm_destroy(mdim_ctx* ctx) {
     for (const Comm::Opened& o : c->opened) cudaIpcCloseMemHandle(o.base);
     if (c->scratch) cudaFree(c->scratch);
     if (c->ring) cudaFree(c->ring);
+    if (c->xchg) cudaFree(c->xchg);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     delete c;
     ctx->comm = nullptr;
@@ -315,12 +320,7 @@ int mdim_fold_sharded_axis(mdim_ctx* ctx, const void* local_rows, uint64_t n_row
         A.init = 0; memcpy(&A.init, &init, (size_t)es);
         A.inbox = c->ring + kRingInboxOff;
         A.next_inbox = (char*)c->ring_peer[next] + kRingInboxOff;
-        A.flag_in = (const uint32_t*)(c->ring + kRingFlagInOff);
-        A.next_flag_in = (uint32_t*)((char*)c->ring_peer[next] + kRingFlagInOff);
-        for (int p = 0; p < c->world; ++p) {
-            A.result[p] = (char*)c->ring_peer[p] + kRingResultOff;
-            A.flag_final[p] = (uint32_t*)((char*)c->ring_peer[p] + kRingFlagFinalOff);
-        }
+        for (int p = 0; p < c->world; ++p) A.result[p] = (char*)c->ring_peer[p] + kRingResultOff;
         A.out = (char*)out_device + c0 * (uint64_t)es;
         A.error = (uint32_t*)(c->ring + kRingErrorOff);
         if (n_cols > kRingCap) return set_error(ctx, MDIM_ERR_UNSUPPORTED, "fold over the sharded axis: more than 2^20 columns per call (strided column windows: fold the result in blocks)");
@@ -334,17 +334,81 @@ int mdim_fold_sharded_axis(mdim_ctx* ctx, const void* local_rows, uint64_t n_row
     return MDIM_OK;
 }
 
+// Collective.  The all-reduce route of the same fold as ONE fused kernel per GPU (csrc/k_fold_xchg.cu):
+//   P_r = rank r's rows folded sequentially (rank 0 from `init`, the others from the operator's identity);
+//   out = ((P_0 (op) P_1) (op) P_2) ... (op) P_{N-1}, the same order on every rank.
+// Bit-identical to the reference for integer / bitwise folds; float sums are reassociated at the rank boundaries only
+// (1e-6 relative) and deterministic.  op: ADD, MUL, AND, OR, XOR.  Asynchronous on the context's stream.
+int mdim_fold_sharded_axis_blocked(mdim_ctx* ctx, const void* local_rows, uint64_t n_rows_local, uint64_t n_cols, int dtype, int op, mdim_scalar init,
+                                   void* out_device) {
+    if (!ctx || !ctx->comm) return ctx ? set_error(ctx, MDIM_ERR_INVALID, "no communicator: call mdim_comm_init") : MDIM_ERR_INVALID;
+    if (!local_rows || !out_device) return MDIM_ERR_INVALID;
+    const int es = dtype_size(dtype);
+    if (es != 4 && es != 8) return set_error(ctx, MDIM_ERR_UNSUPPORTED, "fold over the sharded axis: 4- and 8-byte element types");
+    if (!(op == MDIM_ADD || op == MDIM_MUL || op == MDIM_AND || op == MDIM_OR || op == MDIM_XOR))
+        return set_error(ctx, MDIM_ERR_UNSUPPORTED, "blocked fold over the sharded axis: ADD, MUL, AND, OR, XOR (the operator needs an identity)");
+    if ((dtype == MDIM_F32 || dtype == MDIM_F64) && op >= MDIM_AND) return set_error(ctx, MDIM_ERR_INVALID, "bitwise fold of floats");
+    if (n_cols == 0 || n_rows_local == 0) return set_error(ctx, MDIM_ERR_UNSUPPORTED, "fold over the sharded axis: every rank must hold at least one row");
+    Comm* c = ctx->comm;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t area_bytes = xchg_error_off(c->world) + 256;
+    if (!c->xchg) {  // first use: allocate the packet areas (zero = no epoch), map everyone's into everyone (collective)
+        CU(ctx, cudaMalloc(&c->xchg, area_bytes));
+        CU(ctx, cudaMemsetAsync(c->xchg, 0, area_bytes, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        int st = mdim_peer_table(ctx, c->xchg, area_bytes, c->xchg_peer);
+        if (st) return st;
+        st = mdim_barrier(ctx);
+        if (st) return st;
+    }
+    uint64_t identity = 0;  // x (op) identity == x for EVERY x: for a float sum that is -0.0 (+0.0 would turn a partial of -0.0 into +0.0)
+    if (op == MDIM_ADD && dtype == MDIM_F32) identity = 0x80000000ull;
+    else if (op == MDIM_ADD && dtype == MDIM_F64) identity = 0x8000000000000000ull;
+    else if (op == MDIM_AND) identity = ~0ull;
+    else if (op == MDIM_MUL) {
+        if (dtype == MDIM_F32) { const float one = 1.0f; memcpy(&identity, &one, 4); }
+        else if (dtype == MDIM_F64) { const double one = 1.0; memcpy(&identity, &one, 8); }
+        else identity = 1;
+    }
+    if (es == 4) identity &= 0xffffffffull;
+    const uint64_t row_bytes = n_cols * (uint64_t)es, window = kXchgCapWords * 4;
+    for (uint64_t b0 = 0; b0 < row_bytes; b0 += window) {
+        FoldXchgArgs A;
+        memset(&A, 0, sizeof A);
+        A.n_rows = n_rows_local; A.row_bytes = std::min<uint64_t>(window, row_bytes - b0); A.pitch_bytes = row_bytes;
+        A.rank = c->rank; A.world = c->world;
+        A.epoch = ++c->xchg_epoch; A.slot = A.epoch & 1u;
+        if (c->rank == 0) memcpy(&A.start, &init, (size_t)es); else A.start = identity;
+        A.cap_words = kXchgCapWords;
+        A.rows = (const char*)local_rows + b0;
+        for (int p = 0; p < c->world; ++p) A.area[p] = (char*)c->xchg_peer[p];
+        A.out = (char*)out_device + b0;
+        A.error = (uint32_t*)(c->xchg + xchg_error_off(c->world));
+        const int rc = launch_fold_xchg(A, dtype, op, ctx->sm_count, ctx->stream);
+        if (rc == -1) return set_error(ctx, MDIM_ERR_UNSUPPORTED, "blocked fold over the sharded axis: rows and out 16-byte aligned, row length a multiple of 16 bytes");
+        if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_fold_xchg");
+        ctx->launches++;
+        snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "k_fold_xchg");
+    }
+    poison_inflight(ctx);
+    return MDIM_OK;
+}
+
 // 1 if a fold over the sharded axis gave up waiting for a peer since the last call (then the outputs are garbage)
 int mdim_fold_sharded_axis_status(mdim_ctx* ctx) {
-    if (!ctx || !ctx->comm || !ctx->comm->ring) return MDIM_OK;
-    uint32_t err = 0;
+    if (!ctx || !ctx->comm) return MDIM_OK;
+    Comm* c = ctx->comm;
+    char* words[2] = {c->ring ? c->ring + kRingErrorOff : nullptr, c->xchg ? c->xchg + xchg_error_off(c->world) : nullptr};
+    bool lost = false;
     CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaMemcpyAsync(&err, ctx->comm->ring + kRingErrorOff, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    if (err) {
-        CU(ctx, cudaMemsetAsync(ctx->comm->ring + kRingErrorOff, 0, 4, ctx->stream));
-        return set_error(ctx, MDIM_ERR_NCCL, "fold over the sharded axis: a peer did not arrive within the time limit");
+    for (char* w : words) {
+        if (!w) continue;
+        uint32_t err = 0;
+        CU(ctx, cudaMemcpyAsync(&err, w, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (err) { CU(ctx, cudaMemsetAsync(w, 0, 4, ctx->stream)); lost = true; }
     }
+    if (lost) return set_error(ctx, MDIM_ERR_NCCL, "fold over the sharded axis: a peer did not arrive within the time limit");
     return MDIM_OK;
 }
 
@@ -355,6 +419,9 @@ int mdim_peer_table_close(mdim_ctx* ctx) {
     if (st) return st;
     for (const Comm::Opened& o : ctx->comm->opened) CU(ctx, cudaIpcCloseMemHandle(o.base));
     ctx->comm->opened.clear();
+    // the folds' exchange state was mapped through the same table: drop it, the next fold sets it up again
+    if (ctx->comm->ring) { CU(ctx, cudaFree(ctx->comm->ring)); ctx->comm->ring = nullptr; }
+    if (ctx->comm->xchg) { CU(ctx, cudaFree(ctx->comm->xchg)); ctx->comm->xchg = nullptr; }
     return mdim_barrier(ctx);
 }
 

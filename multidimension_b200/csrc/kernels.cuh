@@ -59,4 +59,7 @@ const char* launch_fold_rows(const FoldRowsPlan& R, void* out, int sm_count, cud
 // ------------------------------------------------------------------------------------------------
 int launch_fold_ring(const FoldRingArgs& A, const void* rows, int sm_count, cudaStream_t stream);
 
+// Fold over the SHARDED axis, blocked by rank + in-kernel all-reduce in rank order over NVLink (k_fold_xchg.cu)
+int launch_fold_xchg(const FoldXchgArgs& A, int dtype, int op, int sm_count, cudaStream_t stream);
+
 }  // namespace mdim

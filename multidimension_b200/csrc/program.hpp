@@ -184,16 +184,29 @@ constexpr uint32_t kPlanScalarOut = 0x10000u;
 struct FoldRingArgs {
     uint64_t n_rows, n_cols;   // this rank's rows x the (unsharded) columns
     int32_t dtype, op, esize, rank, world;
-    uint32_t epoch;            // launch counter of the communicator: flags carry it, so they never need resetting
+    uint32_t epoch;            // launch counter of the communicator: every 16-byte line carries it, so the areas never need resetting
     uint64_t init;             // bits of the fold's initial value (rank 0 starts from it)
-    const void* inbox;         // this GPU's inbox: running values written by rank - 1
+    const void* inbox;         // this GPU's inbox: running values written by rank - 1 as {word, epoch, word, epoch} lines (2 x the data bytes)
     void* next_inbox;          // rank + 1's inbox (peer-mapped)
-    const uint32_t* flag_in;   // per slice, set by rank - 1 after its stores
-    uint32_t* next_flag_in;
-    void* result[MDIM_MAX_PEERS];        // every rank's result area (the last rank writes the finished slices into all of them)
-    uint32_t* flag_final[MDIM_MAX_PEERS];
+    void* result[MDIM_MAX_PEERS];        // every rank's result area (the last rank writes the finished slices into all of them, same lines)
     void* out;
     uint32_t* error;           // set to 1 when a peer did not arrive in time
+};
+
+// k_fold_xchg.cu: fold over the sharded axis as per-rank partial folds + an in-kernel all-reduce in RANK ORDER (one fused
+// compute + exchange kernel per GPU; flag-in-data packets through peer-mapped HBM, no fence, no NCCL call)
+struct FoldXchgArgs {
+    uint64_t n_rows, row_bytes, pitch_bytes;  // this rank's rows; bytes of one row that take part (multiple of 16); bytes between rows
+    int32_t rank, world;
+    uint32_t epoch;            // launch counter: the packets carry it, so the areas never need resetting
+    int32_t wide;              // rows and pitch are 32-byte aligned: 256-bit loads
+    uint32_t slot;             // epoch & 1: two sets of areas alternate, so a rank one launch ahead cannot overwrite unread packets
+    uint64_t start;            // bits of the value this rank's chain starts from (rank 0: init; others: the operator's identity)
+    uint64_t cap_words;        // 32-bit words of one (slot, source rank) area
+    const void* rows;
+    char* area[MDIM_MAX_PEERS];  // every rank's packet area (peer-mapped; area[rank] is local)
+    void* out;
+    uint32_t* error;           // set to 1 when a peer's packets did not arrive in time
 };
 
 struct Plan {

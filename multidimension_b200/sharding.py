@@ -177,8 +177,10 @@ class Comm:
         self.ctx.check(self.ctx.lib.mdim_allreduce(self.ctx.handle, C.c_void_p(storage.dptr), storage.n, storage.dtype, code))
         return storage
 
-    def fold_sharded_axis(self, local_rows, n_rows_local, n_cols, op, init, out=None):
-        """`mdim_fold_sharded_axis`: the fold over the SHARDED (outermost) axis, bit-identical to the reference's sequential
+    def fold_sharded_axis(self, local_rows, n_rows_local, n_cols, op, init, out=None, blocked=False):
+        """`blocked=True`: `mdim_fold_sharded_axis_blocked` — per-rank sequential partial folds combined in rank order by an
+        in-kernel all-reduce over NVLink (csrc/k_fold_xchg.cu): bit-identical for integer folds, reassociated at the rank
+        boundaries (1e-6 relative, deterministic) for float folds.  Otherwise `mdim_fold_sharded_axis`: the fold over the SHARDED (outermost) axis, bit-identical to the reference's sequential
         chain, as one fused kernel per GPU that hands the running values from rank to rank over NVLink (csrc/k_fold_ring.cu).
         `local_rows`: this rank's rows, a device-resident Storage of n_rows_local x n_cols elements; `op`: ops.Add / Sub / Mul /
         BitAnd / BitOr / BitXor; -> the Storage of the n_cols results (on every rank).  Asynchronous on the context's stream."""
@@ -189,11 +191,11 @@ class Comm:
         out = out or Storage.device(self.ctx, local_rows.dtype, n_cols)
         imm = F.Scalar()
         imm.u64 = L.imm_bits(local_rows.dtype, init)
-        self.ctx.check(self.ctx.lib.mdim_fold_sharded_axis(self.ctx.handle, C.c_void_p(local_rows.dptr), n_rows_local, n_cols, local_rows.dtype, op.code, imm,
-                                                           C.c_void_p(out.dptr)))
+        fn = self.ctx.lib.mdim_fold_sharded_axis_blocked if blocked else self.ctx.lib.mdim_fold_sharded_axis
+        self.ctx.check(fn(self.ctx.handle, C.c_void_p(local_rows.dptr), n_rows_local, n_cols, local_rows.dtype, op.code, imm, C.c_void_p(out.dptr)))
         return out
 
-    def prepare_fold_sharded_axis(self, local_rows, n_rows_local, n_cols, op, init, out=None):
+    def prepare_fold_sharded_axis(self, local_rows, n_rows_local, n_cols, op, init, out=None, blocked=False):
         """The same call with its arguments bound once: -> (run, out Storage); `run()` is a single C-ABI call (a 30 us kernel
         must not wait for Python to rebuild its arguments)."""
         import ctypes as C
@@ -203,7 +205,7 @@ class Comm:
         out = out or Storage.device(self.ctx, local_rows.dtype, n_cols)
         imm = F.Scalar()
         imm.u64 = L.imm_bits(local_rows.dtype, init)
-        fn, check = self.ctx.lib.mdim_fold_sharded_axis, self.ctx.check
+        fn, check = (self.ctx.lib.mdim_fold_sharded_axis_blocked if blocked else self.ctx.lib.mdim_fold_sharded_axis), self.ctx.check
         args = (self.ctx.handle, C.c_void_p(local_rows.dptr), C.c_uint64(n_rows_local), C.c_uint64(n_cols), C.c_int(local_rows.dtype), C.c_int(op.code), imm, C.c_void_p(out.dptr))
 
         def run():

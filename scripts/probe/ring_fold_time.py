@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Times mdim_fold_sharded_axis (k_fold_ring) at world = 1 — the pipelined fold kernel without peers — against the
-evaluator's strided fold of the same data: (rows, 262144) f32, rows = 1024 / 512 / 128 (what 1 / 2 / 8 ranks hold of config 4)."""
+"""Times mdim_fold_sharded_axis (k_fold_ring) and mdim_fold_sharded_axis_blocked (k_fold_xchg) at world = 1 — the fold kernels
+without peers — against the evaluator's strided fold of the same data: (rows, 262144) f32, rows = 1024 / 512 / 128 (what 1 / 2 / 8
+ranks hold of config 4).  Successive launches walk through different blocks of a 1 GiB buffer, so nothing is re-read from L2."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -21,25 +22,35 @@ big = torch.empty(1024 * C_, device="cuda", dtype=torch.float32).uniform_(0, 1)
 out = torch.empty(C_, device="cuda", dtype=torch.float32)
 torch.cuda.synchronize()
 for rows in (1024, 512, 128):
-    st = Storage.wrap_device(ctx, F.F32, rows * C_, big.data_ptr(), keep=big)
+    n_blk = 1024 // rows
     so = Storage.wrap_device(ctx, F.F32, C_, out.data_ptr(), keep=out)
-    a = Array.from_device((usize, usize), (rows, C_), big.data_ptr(), "f32", ctx=ctx, keep=big)
-    ev = fold_rows(a.transpose((), usize, usize, ()).iso((usize, usize)), usize, usize, Add, np.float32(0))
     ref = torch.empty(C_, device="cuda", dtype=torch.float32)
-    pe = ev.prepare(out=Storage.wrap_device(ctx, F.F32, C_, ref.data_ptr(), keep=ref), flags=F.COLLECT_ASYNC)
-    ring_run, _ = comm.prepare_fold_sharded_axis(st, rows, C_, Add, np.float32(0), out=so)
-    for name, fn in (("k_fold_ring", ring_run), ("evaluator", pe.run)):
-        for _ in range(3):
-            fn()
+    runs = {"k_fold_ring": [], "k_fold_xchg": [], "evaluator": []}
+    for b in range(n_blk):
+        ptr = big.data_ptr() + 4 * b * rows * C_
+        st = Storage.wrap_device(ctx, F.F32, rows * C_, ptr, keep=big)
+        a = Array.from_device((usize, usize), (rows, C_), ptr, "f32", ctx=ctx, keep=big)
+        ev = fold_rows(a.transpose((), usize, usize, ()).iso((usize, usize)), usize, usize, Add, np.float32(0))
+        runs["evaluator"].append(ev.prepare(out=Storage.wrap_device(ctx, F.F32, C_, ref.data_ptr(), keep=ref), flags=F.COLLECT_ASYNC).run)
+        runs["k_fold_ring"].append(comm.prepare_fold_sharded_axis(st, rows, C_, Add, np.float32(0), out=so)[0])
+        runs["k_fold_xchg"].append(comm.prepare_fold_sharded_axis(st, rows, C_, Add, np.float32(0), out=so, blocked=True)[0])
+    for name, fns in runs.items():
+        for k in range(3):
+            fns[k % n_blk]()
         ctx.sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 16
         e0.record(stream)
-        for _ in range(10):
-            fn()
+        for k in range(reps):
+            fns[k % n_blk]()
         e1.record(stream)
         ctx.sync(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
+        ms = e0.elapsed_time(e1) / reps
         print(f"rows {rows:5d} x {C_} f32  {name:12s} {ms:.4f} ms  {4 * rows * C_ / ms / 1e6:.0f} GB/s", flush=True)
     comm.fold_status()
-    assert torch.equal(out, ref), "ring fold differs from the evaluator's sequential fold"
+    runs["evaluator"][0](); ctx.sync()
+    for name in ("k_fold_ring", "k_fold_xchg"):
+        out.zero_(); torch.cuda.synchronize()
+        runs[name][0](); ctx.sync()
+        assert torch.equal(out, ref), f"{name} differs from the evaluator's sequential fold"
 print("bit-exact against the evaluator at every size")

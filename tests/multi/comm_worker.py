@@ -83,6 +83,16 @@ def main():
     out["fold_ring_u64_xor"] = comm.fold_sharded_axis(odd.storage, ib, 1028, P.BitXor, 0).to_numpy()
     comm.fold_status()
 
+    # (4'') the all-reduce route as ONE fused kernel (k_fold_xchg): per-rank sequential partials combined in rank order
+    out["fold_blocked"] = comm.fold_sharded_axis(A.storage, ib, J * K, Add, np.float32(0.125), blocked=True).to_numpy()
+    out["fold_blocked_f64_mul_init"] = comm.fold_sharded_axis(A64.storage, ib, J * K, P.Mul, 0.5, blocked=True).to_numpy()
+    out["fold_blocked_u64_xor"] = comm.fold_sharded_axis(odd.storage, ib, 1028, P.BitXor, 0, blocked=True).to_numpy()
+    i32_vals = np.random.default_rng([9, rank]).integers(-2**31, 2**31, ib * 4124).astype(np.int32)   # 16496-byte rows: 16-byte aligned only, half group at the end
+    i32 = Array.new((usize, usize), (ib, 4124), i32_vals, "i32").to_device(ctx)
+    for _ in range(3):  # back to back: the packet areas alternate
+        out["fold_blocked_i32_add"] = comm.fold_sharded_axis(i32.storage, ib, 4124, Add, np.int32(-7), blocked=True).to_numpy()
+    comm.fold_status()
+
     # (5) all-reduce with the other operators / dtypes
     mine_vals = np.array([rank + 1, 10 - rank, 7], dtype=np.int64)
     for op in ("sum", "prod", "min", "max"):

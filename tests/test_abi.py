@@ -175,3 +175,14 @@ def test_descriptor_limits_are_declined_cleanly():
     with pytest.raises((P.MdimError, CheckerPanic)) as e:
         emu_collect(many)
     assert e.value.status == F.ERR_UNSUPPORTED
+
+
+def test_fold_over_the_sharded_axis_has_both_routes_behind_the_c_abi():
+    """SURVEY.md 8(e) last row: the bit-exact ring route and the blocked (all-reduce) route are both C-ABI entry points
+    with the same argument list (include/mdim.h), so a host picks the route by name, not by linking NCCL."""
+    import ctypes as C
+    import multidimension_b200 as P
+    lib = C.CDLL(P.LIB_PATH)
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "mdim.h")).read()
+    for name in ("mdim_fold_sharded_axis", "mdim_fold_sharded_axis_blocked", "mdim_fold_sharded_axis_status"):
+        assert hasattr(lib, name) and f"int {name}(" in header

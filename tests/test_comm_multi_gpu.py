@@ -64,6 +64,27 @@ def test_c_abi_collectives_and_peer_tables(world, tmp_path):
         assert_same_bits(p["fold_ring"], seq, "ring fold over the sharded axis (f32 add)")
         assert_same_bits(p["fold_ring_f64_mul_init"], seq64, "ring fold (f64 mul, init 0.5)")
         assert_same_bits(p["fold_ring_u64_xor"], want_xor, "ring fold (u64 xor, ragged slice)")
+    # the blocked route: P_r sequential (rank 0 from init, the others from the identity), combined in rank order — restated here
+    rows = a.reshape(world, ib, J * K)
+    blocked, blocked64 = None, None
+    for r in range(world):
+        pr = np.full(J * K, np.float32(0.125) if r == 0 else np.float32(-0.0))
+        pr64 = np.full(J * K, 0.5 if r == 0 else 1.0)
+        for i in range(ib):
+            pr = pr + rows[r, i]
+            pr64 = pr64 * (rows[r, i].astype(np.float64) * 3.0)
+        blocked = pr if r == 0 else blocked + pr
+        blocked64 = pr64 if r == 0 else blocked64 * pr64
+    want_i32 = np.full(4124, -7, np.int64)
+    for r in range(world):
+        want_i32 += np.random.default_rng([9, r]).integers(-2**31, 2**31, ib * 4124).astype(np.int32).reshape(ib, 4124).astype(np.int64).sum(axis=0)
+    want_i32 = want_i32.astype(np.int32)  # wrapping
+    for p in parts:
+        assert_same_bits(p["fold_blocked"], blocked, "blocked fold (f32 add, init 0.125): the rank-ordered combination, bit for bit")
+        assert np.max(np.abs(p["fold_blocked"] - (seq + np.float32(0.125))) / np.abs(seq)) <= 1e-6
+        assert_same_bits(p["fold_blocked_f64_mul_init"], blocked64, "blocked fold (f64 mul, init 0.5)")
+        assert_same_bits(p["fold_blocked_u64_xor"], want_xor, "blocked fold (u64 xor): associative, identical to the reference")
+        assert_same_bits(p["fold_blocked_i32_add"], want_i32, "blocked fold (i32 wrapping add, rows 16-byte aligned only)")
     ranks = np.arange(world)
     for p in parts:
         assert p["ar_sum"].tolist() == [int((ranks + 1).sum()), int((10 - ranks).sum()), 7 * world]
@@ -109,5 +130,33 @@ def test_ring_fold_single_rank_is_the_sequential_fold():
         for i in range(rows):
             want = want + x.reshape(rows, cols)[i]
         assert_same_bits(got, want, f"ring fold {rows}x{cols}")
+    comm.close()
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_blocked_fold_single_rank_is_the_sequential_fold():
+    """world = 1: k_fold_xchg alone (column walk with 256-bit loads, packets through the local area), no peers."""
+    import multidimension_b200 as P
+    from multidimension_b200 import _ffi as F
+    from multidimension_b200.runtime import Storage
+    from multidimension_b200.sharding import Comm
+    ctx = P.Context(0)
+    comm = Comm(ctx, 0, 1, Comm.unique_id())
+    rng = np.random.default_rng(12)
+    for rows, cols, dt, npdt in ((100, 4096, F.F32, np.float32), (33, 1028, F.F32, np.float32), (257, 516, F.F64, np.float64), (1, 8, F.F32, np.float32),
+                                 (40, (1 << 20) + 72, F.F32, np.float32)):  # the last one: wider than one packet area -> two launches
+        x = rng.uniform(0, 1, rows * cols).astype(npdt)
+        st = Storage.device(ctx, dt, rows * cols)
+        ctx.upload(st.dptr, x)
+        got = comm.fold_sharded_axis(st, rows, cols, P.Add, npdt(0.25), blocked=True).to_numpy()
+        comm.fold_status()
+        assert ctx.last_kernel() == "k_fold_xchg"
+        want = np.full(cols, npdt(0.25))
+        for i in range(rows):
+            want = want + x.reshape(rows, cols)[i]
+        assert_same_bits(got, want, f"blocked fold {rows}x{cols}")
+    with pytest.raises(F.MdimError):
+        comm.fold_sharded_axis(st, rows, cols, P.Sub, npdt(0), blocked=True)  # no identity: the ring route serves SUB
     comm.close()
     ctx.close()
