@@ -179,6 +179,16 @@ int launch_plan(mdim_ctx* ctx, const Plan& p, void* out, ErrWord* err) {
             CU(ctx, cudaGetLastError());
             return MDIM_OK;
         }
+        case KK_FOLD_COLS: {
+            FoldColsPlan fc = p.fc;
+            fc.nowait = nowait;
+            const char* name = launch_fold_cols(fc, out, ctx->stream);
+            if (!name) return cuda_fail(ctx, cudaGetLastError(), "k_fold_cols");
+            snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "%s", name);
+            ctx->launches++;
+            CU(ctx, cudaGetLastError());
+            return MDIM_OK;
+        }
         default: return launch_eval(ctx, p, out, err, false, 0, nowait);
     }
 }
@@ -443,7 +453,7 @@ int mdim_collect(mdim_ctx* ctx, const mdim_expr* e, void* out_device, uint32_t f
     if (plan->kind != KK_EMPTY && !out_device) { delete plan; return set_error(ctx, MDIM_ERR_INVALID, "null output buffer"); }
     if (plan->kind != KK_EMPTY && plan->n_out > 1) { delete plan; return set_error(ctx, MDIM_ERR_INVALID, "a tuple-typed root needs mdim_collect_tuple (one output run per scalar leaf)"); }
     if (plan->kind != KK_EMPTY && ((uintptr_t)out_device % (uintptr_t)plan->out_esize) != 0) { delete plan; return set_error(ctx, MDIM_ERR_INVALID, "output buffer is not aligned to its element size"); }
-    if (plan->kind != KK_EMPTY && ((uintptr_t)out_device % 16) != 0 && (plan->vec > 1 || plan->kind == KK_FOLD_ROWS)) {
+    if (plan->kind != KK_EMPTY && ((uintptr_t)out_device % 16) != 0 && (plan->vec > 1 || plan->kind == KK_FOLD_ROWS || plan->kind == KK_FOLD_COLS)) {
         // an element-aligned output (a slice of a caller's tensor): plan again with scalar stores
         st = plan_expr(e, flags | kPlanScalarOut, plan, why, sizeof why);
         if (st) { delete plan; return set_error(ctx, st, why); }

@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "exec.cuh"
 #include "kernels.cuh"
@@ -65,10 +66,12 @@ template <class S> __device__ __forceinline__ void pack(const S (&v)[32 / sizeof
 }
 
 // S = slot type (raw bits), DT / OP compile-time (bin_op's switches fold away), ROWS = rows in flight per thread
-template <class S, int DT, int OP, int ROWS>
-__global__ void __launch_bounds__(kXThreads) k_fold_xchg(const __grid_constant__ FoldXchgArgs A) {
+// EXCHANGE = false: the column walk alone (one GPU, KK_FOLD_COLS): the chain's values ARE the result.
+template <class S, int DT, int OP, int ROWS, bool EXCHANGE>
+// min blocks per SM = ptxas's register budget (168 / 255): left to itself it settles at ~56 registers with 2-3 loads in flight (4.1 TB/s)
+__global__ void __launch_bounds__(kXThreads, EXCHANGE ? 4 : 6) k_fold_xchg(const __grid_constant__ FoldXchgArgs A) {
     constexpr int EPT = 32 / (int)sizeof(S);
-    pdl_entry(false);  // reads the caller's rows: always waits for its predecessor in the stream
+    pdl_entry(!EXCHANGE && A.nowait != 0);  // the exchange form always waits for its predecessor in the stream
     const uint64_t n_groups = (A.row_bytes + 31) / 32;  // 32-byte column groups (the last one may be half: row_bytes % 16 == 0)
     const uint64_t n_slices = (n_groups + kXThreads - 1) / kXThreads;
     for (uint64_t slice = blockIdx.x; slice < n_slices; slice += gridDim.x) {
@@ -83,25 +86,44 @@ __global__ void __launch_bounds__(kXThreads) k_fold_xchg(const __grid_constant__
         // ---- this rank's rows, in order ------------------------------------------------------------------------------------
         const char* p = (const char*)A.rows + b0;
         uint64_t r = 0;
-        if (full) {
-            for (; r + ROWS <= A.n_rows; r += ROWS) {
-                uint32_t x[ROWS][8];
+        // A rolling window of ROWS loads in flight per thread: row r is folded, then its registers are refilled with row r + ROWS
+        // (a batch of loads followed by a batch of adds drains the memory pipeline between batches: 6.0 vs 6.9 TB/s).  The alignment
+        // test is hoisted out of the loop.
+        auto walk = [&](auto wide_tag) {
+            constexpr bool WIDE = decltype(wide_tag)::value;
+            if (A.n_rows < (uint64_t)ROWS) return;  // short blocks: the row-at-a-time loop below
+            uint32_t x[ROWS][8];
+#define MDIM_LOAD_ROW(u, row)                                                                                  \
+    do {                                                                                                       \
+        if constexpr (WIDE) ld256_stream(p + (row) * A.pitch_bytes, x[u]);                                     \
+        else { /* rows only 16-byte aligned: two 128-bit loads */                                              \
+            ld128_stream(p + (row) * A.pitch_bytes, x[u][0], x[u][1], x[u][2], x[u][3]);                       \
+            ld128_stream(p + (row) * A.pitch_bytes + 16, x[u][4], x[u][5], x[u][6], x[u][7]);                  \
+        }                                                                                                      \
+    } while (0)
+#define MDIM_FOLD_ROW(u)                                                                                       \
+    do {                                                                                                       \
+        S v[EPT];                                                                                              \
+        unpack<S>(x[u], v);                                                                                    \
+        _Pragma("unroll") for (int e = 0; e < EPT; ++e) { bool arith = false; acc[e] = bin_op<S>(DT, OP, DT, acc[e], v[e], arith); } \
+    } while (0)
+#pragma unroll
+            for (int u = 0; u < ROWS; ++u) MDIM_LOAD_ROW(u, (uint64_t)u);
+            for (; r + 2 * ROWS <= A.n_rows; r += ROWS) {
 #pragma unroll
                 for (int u = 0; u < ROWS; ++u) {
-                    if (A.wide) ld256_stream(p + (r + u) * A.pitch_bytes, x[u]);
-                    else {  // rows only 16-byte aligned: two 128-bit loads
-                        ld128_stream(p + (r + u) * A.pitch_bytes, x[u][0], x[u][1], x[u][2], x[u][3]);
-                        ld128_stream(p + (r + u) * A.pitch_bytes + 16, x[u][4], x[u][5], x[u][6], x[u][7]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < ROWS; ++u) {
-                    S v[EPT];
-                    unpack<S>(x[u], v);
-#pragma unroll
-                    for (int e = 0; e < EPT; ++e) { bool arith = false; acc[e] = bin_op<S>(DT, OP, DT, acc[e], v[e], arith); }
+                    MDIM_FOLD_ROW(u);
+                    MDIM_LOAD_ROW(u, r + ROWS + u);
                 }
             }
+#pragma unroll
+            for (int u = 0; u < ROWS; ++u) MDIM_FOLD_ROW(u);  // the window's last rows
+            r += ROWS;
+#undef MDIM_LOAD_ROW
+#undef MDIM_FOLD_ROW
+        };
+        if (full) {
+            if (A.wide) walk(std::true_type{}); else walk(std::false_type{});
         }
         for (; r < A.n_rows; ++r) {
             uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -115,9 +137,16 @@ __global__ void __launch_bounds__(kXThreads) k_fold_xchg(const __grid_constant__
         // ---- exchange.  Two ranks: everybody sends to everybody and combines (one hop).  More: the columns have an OWNER (warp-
         //      granular, round robin) that collects the partial values, combines them in rank order and sends the result to
         //      everybody: two hops, but 2 (N-1)/N of a row per GPU over NVLink instead of N-1 rows ---------------------------------
+        if constexpr (!EXCHANGE) {
+            uint32_t ow[8];
+            pack<S>(acc, ow);
+            st128((char*)A.out + b0, ow[0], ow[1], ow[2], ow[3], false);
+            if (full) st128((char*)A.out + b0 + 16, ow[4], ow[5], ow[6], ow[7], false);
+            continue;
+        }
         uint32_t w[8];
         pack<S>(acc, w);
-        const bool one_shot = A.world <= 2;
+        const bool one_shot = A.one_shot != 0;
         const int owner = one_shot ? A.rank : (int)((g >> 5) % (uint64_t)A.world);
         const uint64_t slot_base = (uint64_t)A.slot * (A.world + 1) * A.cap_words * 8;   // [slot][source rank 0..N-1, then the results][cap_words x 8 B]
         {
@@ -215,22 +244,35 @@ __global__ void __launch_bounds__(kXThreads) k_fold_xchg(const __grid_constant__
 
 using XchgKernel = void (*)(const FoldXchgArgs);
 
-template <class S, int DT, int kXRows> XchgKernel pick_op(int op) {
+template <class S, int DT, int kXRows, bool EXCHANGE> XchgKernel pick_op(int op) {
     constexpr bool is_float = DT == MDIM_F32 || DT == MDIM_F64;
     switch (op) {
-        case MDIM_ADD: return k_fold_xchg<S, DT, MDIM_ADD, kXRows>;
-        case MDIM_MUL: return k_fold_xchg<S, DT, MDIM_MUL, kXRows>;
+        case MDIM_ADD: return k_fold_xchg<S, DT, MDIM_ADD, kXRows, EXCHANGE>;
+        case MDIM_MUL: return k_fold_xchg<S, DT, MDIM_MUL, kXRows, EXCHANGE>;
         default: break;
+    }
+    if constexpr (!EXCHANGE) {  // no identity: a chain, but nothing to combine partial results with
+        if (op == MDIM_SUB) return k_fold_xchg<S, DT, MDIM_SUB, kXRows, EXCHANGE>;
     }
     if constexpr (!is_float) {
         switch (op) {
-            case MDIM_AND: return k_fold_xchg<S, DT, MDIM_AND, kXRows>;
-            case MDIM_OR: return k_fold_xchg<S, DT, MDIM_OR, kXRows>;
-            case MDIM_XOR: return k_fold_xchg<S, DT, MDIM_XOR, kXRows>;
+            case MDIM_AND: return k_fold_xchg<S, DT, MDIM_AND, kXRows, EXCHANGE>;
+            case MDIM_OR: return k_fold_xchg<S, DT, MDIM_OR, kXRows, EXCHANGE>;
+            case MDIM_XOR: return k_fold_xchg<S, DT, MDIM_XOR, kXRows, EXCHANGE>;
             default: break;
         }
     }
     return nullptr;
+}
+
+template <bool EXCHANGE> XchgKernel pick_kernel(int dtype, int op) {
+    switch (dtype) {  // wrapping integer + - * and the bitwise operators do not care about the sign: one instantiation per width
+        case MDIM_F32: return pick_op<uint32_t, MDIM_F32, 12, EXCHANGE>(op);  // 12 rows in flight per thread: 3 / 4 / 6 / 8 / 12 / 16 -> 4.5 / 5.4 / 6.5 / 7.0 / 7.25 / 6.0 TB/s (profiles/)
+        case MDIM_I32: case MDIM_U32: return pick_op<uint32_t, MDIM_U32, 12, EXCHANGE>(op);
+        case MDIM_F64: return pick_op<uint64_t, MDIM_F64, 12, EXCHANGE>(op);
+        case MDIM_I64: case MDIM_U64: return pick_op<uint64_t, MDIM_U64, 12, EXCHANGE>(op);
+        default: return nullptr;
+    }
 }
 
 }  // namespace
@@ -239,18 +281,11 @@ template <class S, int DT, int kXRows> XchgKernel pick_op(int op) {
 int launch_fold_xchg(const FoldXchgArgs& A, int dtype, int op, int sm_count, cudaStream_t stream) {
     if (((uintptr_t)A.rows & 15) || (A.pitch_bytes & 15) || (A.row_bytes & 15) || ((uintptr_t)A.out & 15) || !A.n_rows || !A.row_bytes) return -1;
     FoldXchgArgs B = A;
+    // two ranks: one hop; more: owners (two hops, 2 (N-1)/N rows per GPU over NVLink instead of N-1).  MDIM_XCHG_ONE_SHOT=0/1 forces either.
+    static const int forced = [] { const char* e = getenv("MDIM_XCHG_ONE_SHOT"); return e ? atoi(e) : -1; }();
+    B.one_shot = forced >= 0 ? forced : (A.world <= 2);
     B.wide = !(((uintptr_t)A.rows & 31) || (A.pitch_bytes & 31));
-    XchgKernel fn = nullptr;
-#define PICK(R)                                                                                                  \
-    switch (dtype) { /* wrapping integer + * and the bitwise operators do not care about the sign: one instantiation per width */ \
-        case MDIM_F32: fn = pick_op<uint32_t, MDIM_F32, R>(op); break;                                           \
-        case MDIM_I32: case MDIM_U32: fn = pick_op<uint32_t, MDIM_U32, R>(op); break;                            \
-        case MDIM_F64: fn = pick_op<uint64_t, MDIM_F64, R>(op); break;                                           \
-        case MDIM_I64: case MDIM_U64: fn = pick_op<uint64_t, MDIM_U64, R>(op); break;                            \
-        default: break;                                                                                          \
-    }
-    PICK(16)  // rows in flight per thread (8: the same rate, profiles/r2_ring_fold_time.log)
-#undef PICK
+    XchgKernel fn = pick_kernel<true>(dtype, op);
     if (!fn) return -1;
     static XchgKernel known_fn[32];
     static int known_per_sm[32], n_known = 0;  // the context is single-threaded (mdim.h)
@@ -268,6 +303,20 @@ int launch_fold_xchg(const FoldXchgArgs& A, int dtype, int op, int sm_count, cud
     const int grid = (int)std::min<uint64_t>(n_slices, (uint64_t)per_sm * (uint64_t)sm_count);
     e = launch_pdl(fn, dim3(grid), dim3(kXThreads), 0, stream, B);
     return e == cudaSuccess ? 0 : (int)e;
+}
+
+// The column walk on one GPU (KK_FOLD_COLS, planned in plan.cpp): no packets, no co-residency requirement.
+const char* launch_fold_cols(const FoldColsPlan& C, void* out, cudaStream_t stream) {
+    XchgKernel fn = pick_kernel<false>(C.dtype, C.op);
+    if (!fn) return nullptr;
+    FoldXchgArgs A;
+    memset(&A, 0, sizeof A);
+    A.n_rows = C.n_rows; A.row_bytes = C.row_bytes; A.pitch_bytes = C.pitch_bytes;
+    A.world = 1; A.start = C.init; A.rows = C.src; A.out = out; A.nowait = C.nowait;
+    A.wide = !(((uintptr_t)C.src & 31) || (C.pitch_bytes & 31));
+    const uint64_t n_groups = (C.row_bytes + 31) / 32, n_slices = (n_groups + kXThreads - 1) / kXThreads;
+    const int grid = (int)std::min<uint64_t>(n_slices, 1u << 30);
+    return launch_pdl(fn, dim3(grid), dim3(kXThreads), 0, stream, A) == cudaSuccess ? "k_fold_cols" : nullptr;
 }
 
 }  // namespace mdim

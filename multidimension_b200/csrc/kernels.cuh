@@ -61,5 +61,7 @@ int launch_fold_ring(const FoldRingArgs& A, const void* rows, int sm_count, cuda
 
 // Fold over the SHARDED axis, blocked by rank + in-kernel all-reduce in rank order over NVLink (k_fold_xchg.cu)
 int launch_fold_xchg(const FoldXchgArgs& A, int dtype, int op, int sm_count, cudaStream_t stream);
+// ... and the same column walk on one GPU, no exchange (KK_FOLD_COLS): -> name of the kernel launched, nullptr on a launch error
+const char* launch_fold_cols(const FoldColsPlan& C, void* out, cudaStream_t stream);
 
 }  // namespace mdim

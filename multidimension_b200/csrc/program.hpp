@@ -125,6 +125,7 @@ enum KernelKind : int32_t {
     KK_STREAM = 2,     // rank-<=1 contiguous: k_eval with the decode compiled out
     KK_TRANSPOSE = 3,  // tiled smem transpose of one leaf (k_transpose)
     KK_FOLD_ROWS = 4,  // last-axis sequential fold (+ fused broadcast epilogue) (k_fold_rows)
+    KK_FOLD_COLS = 5,  // sequential fold over an OUTER axis of one leaf whose result is contiguous: a column walk (k_fold_cols)
 };
 
 struct TransposePlan {
@@ -171,6 +172,16 @@ struct FoldRowsPlan {
     int32_t nowait;       // set per launch (api.cu): see launch.cuh
 };
 
+struct FoldColsPlan {
+    const void* src;      // first byte of row 0 (offset applied)
+    uint64_t n_rows;      // reduction length: rows walked in index order
+    uint64_t row_bytes;   // bytes of one row that take part (= bytes of the result; multiple of 16)
+    uint64_t pitch_bytes; // bytes between consecutive rows (multiple of 16)
+    int32_t op, dtype;
+    uint64_t init;
+    int32_t nowait;       // set per launch (api.cu): see launch.cuh
+};
+
 // Memory a launch reads (api.cu adds the output and decides whether the kernel may skip griddepcontrol.wait).
 constexpr uint64_t kGatherBigBytes = 1ull << 30;  // ~8x the 126 MB L2: below that the plain load's L2 hits win (probe)
 constexpr int kMaxRanges = 24;
@@ -200,6 +211,8 @@ struct FoldXchgArgs {
     int32_t rank, world;
     uint32_t epoch;            // launch counter: the packets carry it, so the areas never need resetting
     int32_t wide;              // rows and pitch are 32-byte aligned: 256-bit loads
+    int32_t one_shot;          // every rank sends to every rank and combines (one hop) instead of owners (two hops)
+    int32_t nowait;            // one-GPU form only: the launch is independent of its predecessors (launch.cuh)
     uint32_t slot;             // epoch & 1: two sets of areas alternate, so a rank one launch ahead cannot overwrite unread packets
     uint64_t start;            // bits of the value this rank's chain starts from (rank 0: init; others: the operator's identity)
     uint64_t cap_words;        // 32-bit words of one (slot, source rank) area
@@ -227,6 +240,7 @@ struct Plan {
     Program prog;
     TransposePlan tr;
     FoldRowsPlan fr;
+    FoldColsPlan fc;
     char sig[kMaxInstr * 4 + 4];  // signature bytes (opc,dtype,op,aux per instruction)
     int32_t sig_len;
     char describe[192];

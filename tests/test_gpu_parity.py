@@ -243,6 +243,40 @@ def test_fold_over_outermost_axis(ctx, shape):  # the per-rank partial of a shar
     check(fold_rows(a.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize)), (usize, usize), usize, Mul, np.float32(1)), ctx)
 
 
+def test_fold_over_outer_axis_column_walk(ctx):
+    """KK_FOLD_COLS (k_fold_cols): a sequential fold over an OUTER axis whose result is contiguous is a column walk with 256-bit
+    loads — the one-GPU form of the fold over the sharded axis.  Every dtype / operator it takes, rows 32- and only 16-byte
+    aligned, a column window of a wider Array (row pitch > row length), a tail of rows below the unroll, and the evaluator
+    (NO_FASTPATH) as the second opinion."""
+    rng = np.random.default_rng(77)
+
+    def outer_fold(a, rows, cols, op, init):
+        return fold_rows(a.transpose((), usize, usize, ()).iso((usize, usize)), usize, usize, op, init)
+    for rows, cols in ((100, 64), (37, 1028), (16, 8), (5, 4), (129, 520)):
+        f = Array.new((usize, usize), (rows, cols), rng.uniform(0.9, 1.1, rows * cols).astype(np.float32))
+        for op, init in ((Add, np.float32(0.25)), (Mul, np.float32(1)), (P.Sub, np.float32(3))):
+            v = outer_fold(f, rows, cols, op, init)
+            assert "fold_cols" in v.describe(), v.describe()
+            check(v, ctx)
+            check(v, ctx, F.COLLECT_NO_FASTPATH)
+        seq = np.full(cols, np.float32(0.25))
+        for i in range(rows):
+            seq = seq + f.as_ref().reshape(rows, cols)[i]
+        assert_same_bits(collect(outer_fold(f, rows, cols, Add, np.float32(0.25)), ctx), seq)
+    u = Array.new((usize, usize), (50, 36), rng.integers(0, 1 << 63, 1800).astype(np.uint64), usize)
+    for op, init in ((Add, 7), (Mul, 3), (BitXor, 0), (P.BitAnd, (1 << 64) - 1), (P.BitOr, 0)):
+        check(outer_fold(u, 50, 36, op, init), ctx)
+    i32 = Array.new((usize, usize), (40, 12), rng.integers(-2**31, 2**31, 480).astype(np.int32), "i32")
+    check(outer_fold(i32, 40, 12, Add, np.int32(-5)), ctx)     # wrapping
+    d = Array.new((usize, usize), (33, 10), rng.uniform(0, 1, 330))
+    check(outer_fold(d, 33, 10, Add, 0.5), ctx)
+    # 17 columns: rows not a multiple of 16 bytes -> the evaluator keeps it
+    odd = Array.new((usize, usize), (9, 17), rng.uniform(0, 1, 153).astype(np.float32))
+    v = outer_fold(odd, 9, 17, Add, np.float32(0))
+    assert "fold_cols" not in v.describe()
+    check(v, ctx)
+
+
 # ---- K5: general rank-N evaluator (config 5) ----------------------------------------------------------------------------
 def config5(P_, Q, R, rng):
     a = Array.new((usize, usize), (P_, Q), rand(rng, "f32", P_ * Q))
