@@ -35,7 +35,7 @@ namespace mdim {
 namespace {
 
 constexpr int kXThreads = 64;
-constexpr unsigned long long kXSpinLimit = 20ull * 1000 * 1000;
+constexpr unsigned long long kXSpinLimit = 4ull * 1000 * 1000;  // polling rounds (~0.5 us each): ~2 s
 
 __device__ __forceinline__ void st_line(char* p, uint32_t a, uint32_t b, uint32_t flag) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(flag), "r"(b), "r"(flag) : "memory");
@@ -164,29 +164,34 @@ __global__ void __launch_bounds__(kXThreads, EXCHANGE ? 4 : 6) k_fold_xchg(const
         S tot[EPT];
         bool lost = false;
         if (owner == A.rank) {
-            // every rank's partial values of these columns: all loads first, then re-poll the lines that are not there yet
+            // every rank's partial values of these columns.  Each round re-reads ALL the lines that are not there yet with independent
+            // loads (one memory latency per round; polling line after line costs one latency PER LINE: 32 lines at 8 ranks = 20+ us)
             uint4 L[MDIM_MAX_PEERS][4];
 #pragma unroll
-            for (int q = 0; q < MDIM_MAX_PEERS; ++q)
-                if (q < A.world) {
+            for (int q = 0; q < MDIM_MAX_PEERS; ++q) {
 #pragma unroll
-                    for (int l = 0; l < 4; ++l)
-                        if (l < n_lines) L[q][l] = ld_line(mine + (uint64_t)q * A.cap_words * 8 + 512 * l);
-                }
+                for (int l = 0; l < 4; ++l) L[q][l] = make_uint4(0, ~A.epoch, 0, ~A.epoch);
+            }
+            for (unsigned long long spins = 0;; ++spins) {
 #pragma unroll
-            for (int q = 0; q < MDIM_MAX_PEERS; ++q)
-                if (q < A.world) {
+                for (int q = 0; q < MDIM_MAX_PEERS; ++q)
+                    if (q < A.world) {
 #pragma unroll
-                    for (int l = 0; l < 4; ++l)
-                        if (l < n_lines) {
-                            unsigned long long spins = 0;
-                            while (L[q][l].y != A.epoch || L[q][l].w != A.epoch) {
-                                if (++spins > kXSpinLimit) { lost = true; break; }
-                                if (spins > 8) __nanosleep(32);
-                                L[q][l] = ld_line(mine + (uint64_t)q * A.cap_words * 8 + 512 * l);
-                            }
-                        }
-                }
+                        for (int l = 0; l < 4; ++l)
+                            if (l < n_lines && (L[q][l].y != A.epoch || L[q][l].w != A.epoch)) L[q][l] = ld_line(mine + (uint64_t)q * A.cap_words * 8 + 512 * l);
+                    }
+                bool pending = false;
+#pragma unroll
+                for (int q = 0; q < MDIM_MAX_PEERS; ++q)
+                    if (q < A.world) {
+#pragma unroll
+                        for (int l = 0; l < 4; ++l)
+                            if (l < n_lines && (L[q][l].y != A.epoch || L[q][l].w != A.epoch)) pending = true;
+                    }
+                if (!pending) break;
+                if (spins > kXSpinLimit) { lost = true; break; }
+                if (spins > 4) __nanosleep(64);
+            }
             if (lost) { atomicExch(A.error, 1u); continue; }
             // combine in rank order
 #pragma unroll
@@ -219,19 +224,22 @@ __global__ void __launch_bounds__(kXThreads, EXCHANGE ? 4 : 6) k_fold_xchg(const
             uint32_t pw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             uint4 R[4];
 #pragma unroll
-            for (int l = 0; l < 4; ++l)
-                if (l < n_lines) R[l] = ld_line(mine + (uint64_t)A.world * A.cap_words * 8 + 512 * l);
+            for (int l = 0; l < 4; ++l) R[l] = make_uint4(0, ~A.epoch, 0, ~A.epoch);
+            for (unsigned long long spins = 0;; ++spins) {
+#pragma unroll
+                for (int l = 0; l < 4; ++l)
+                    if (l < n_lines && (R[l].y != A.epoch || R[l].w != A.epoch)) R[l] = ld_line(mine + (uint64_t)A.world * A.cap_words * 8 + 512 * l);
+                bool pending = false;
+#pragma unroll
+                for (int l = 0; l < 4; ++l)
+                    if (l < n_lines && (R[l].y != A.epoch || R[l].w != A.epoch)) pending = true;
+                if (!pending) break;
+                if (spins > kXSpinLimit) { lost = true; break; }
+                if (spins > 4) __nanosleep(64);
+            }
 #pragma unroll
             for (int l = 0; l < 4; ++l)
-                if (l < n_lines) {
-                    unsigned long long spins = 0;
-                    while (R[l].y != A.epoch || R[l].w != A.epoch) {
-                        if (++spins > kXSpinLimit) { lost = true; break; }
-                        if (spins > 8) __nanosleep(32);
-                        R[l] = ld_line(mine + (uint64_t)A.world * A.cap_words * 8 + 512 * l);
-                    }
-                    pw[2 * l] = R[l].x; pw[2 * l + 1] = R[l].z;
-                }
+                if (l < n_lines) { pw[2 * l] = R[l].x; pw[2 * l + 1] = R[l].z; }
             if (lost) { atomicExch(A.error, 1u); continue; }
             unpack<S>(pw, tot);
         }
