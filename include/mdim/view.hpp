@@ -717,6 +717,10 @@ struct Api {
     int (*comm_unique_id)(uint8_t*) = nullptr; int (*comm_init)(mdim_ctx*, int, int, const uint8_t*) = nullptr; int (*comm_destroy)(mdim_ctx*) = nullptr;
     int (*allgather)(mdim_ctx*, const void*, void*, size_t) = nullptr; int (*allreduce)(mdim_ctx*, void*, size_t, int, int) = nullptr; int (*barrier)(mdim_ctx*) = nullptr;
     int (*peer_table)(mdim_ctx*, void*, size_t, void**) = nullptr; int (*peer_table_close)(mdim_ctx*) = nullptr;
+    // fold over the sharded axis as ONE fused compute + exchange kernel per GPU: the bit-exact chain through the ranks, and the blocked (all-reduce) route
+    int (*fold_sharded_axis)(mdim_ctx*, const void*, uint64_t, uint64_t, int, int, mdim_scalar, void*) = nullptr;
+    int (*fold_sharded_axis_blocked)(mdim_ctx*, const void*, uint64_t, uint64_t, int, int, mdim_scalar, void*) = nullptr;
+    int (*fold_sharded_axis_status)(mdim_ctx*) = nullptr;
     template <class Sym> static Api load(Sym&& sym) {  // sym(name) -> void*
         Api a;
 #define MDIM_API(field, name) a.field = reinterpret_cast<decltype(a.field)>(sym(name))
@@ -726,6 +730,8 @@ struct Api {
         MDIM_API(comm_unique_id, "mdim_comm_unique_id"); MDIM_API(comm_init, "mdim_comm_init"); MDIM_API(comm_destroy, "mdim_comm_destroy");
         MDIM_API(allgather, "mdim_allgather"); MDIM_API(allreduce, "mdim_allreduce"); MDIM_API(barrier, "mdim_barrier");
         MDIM_API(peer_table, "mdim_peer_table"); MDIM_API(peer_table_close, "mdim_peer_table_close");
+        MDIM_API(fold_sharded_axis, "mdim_fold_sharded_axis"); MDIM_API(fold_sharded_axis_blocked, "mdim_fold_sharded_axis_blocked");
+        MDIM_API(fold_sharded_axis_status, "mdim_fold_sharded_axis_status");
 #undef MDIM_API
         return a;
     }

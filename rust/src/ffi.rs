@@ -100,6 +100,11 @@ extern "C" {
     pub fn mdim_barrier(ctx: *mut MdimCtx) -> i32;
     pub fn mdim_peer_table(ctx: *mut MdimCtx, local_device: *mut c_void, block_bytes: usize, peers: *mut *mut c_void) -> i32;
     pub fn mdim_peer_table_close(ctx: *mut MdimCtx) -> i32;
+    // fold over the sharded (outermost) axis as one fused compute + exchange kernel per GPU: the reference's sequential chain through the
+    // ranks (bit-exact), and per-rank partial folds combined in rank order inside the kernel (the all-reduce route, no NCCL call)
+    pub fn mdim_fold_sharded_axis(ctx: *mut MdimCtx, local_rows: *const c_void, n_rows_local: u64, n_cols: u64, dtype: i32, op: i32, init: MdimScalar, out_device: *mut c_void) -> i32;
+    pub fn mdim_fold_sharded_axis_blocked(ctx: *mut MdimCtx, local_rows: *const c_void, n_rows_local: u64, n_cols: u64, dtype: i32, op: i32, init: MdimScalar, out_device: *mut c_void) -> i32;
+    pub fn mdim_fold_sharded_axis_status(ctx: *mut MdimCtx) -> i32;
     pub fn mdim_ipc_export(ctx: *mut MdimCtx, dptr: *mut c_void, handle: *mut u8) -> i32;
     pub fn mdim_ipc_open(ctx: *mut MdimCtx, handle: *const u8, dptr: *mut *mut c_void) -> i32;
     pub fn mdim_ipc_close(ctx: *mut MdimCtx, dptr: *mut c_void) -> i32;

@@ -77,6 +77,35 @@ int main(int argc, char** argv) {
     }
     CHECK(same);
 
+    // (4) the same fold as ONE fused kernel per GPU, both routes: the bit-exact chain through the ranks (k_fold_ring) equals the
+    //     sequential f32 sum over ALL rows in index order; the blocked route (k_fold_xchg) equals the per-rank sequential partial sums
+    //     (rank 0 from the initial value, the others from -0.0) combined in rank order — both restated here, bit for bit
+    {
+        DeviceArray<usize, float> ring(api, ctx, N), blocked(api, ctx, N);
+        mdim_scalar init; std::memset(&init, 0, sizeof init); init.f32 = 0.5f;
+        api.check(ctx, api.fold_sharded_axis(ctx, local.device_ptr(), M / (uint64_t)world, N, MDIM_F32, MDIM_ADD, init, ring.device_ptr()));
+        api.check(ctx, api.fold_sharded_axis_blocked(ctx, local.device_ptr(), M / (uint64_t)world, N, MDIM_F32, MDIM_ADD, init, blocked.device_ptr()));
+        api.check(ctx, api.fold_sharded_axis_status(ctx));
+        api.check(ctx, api.sync(ctx));
+        auto got_ring = ring.to_raw(), got_blocked = blocked.to_raw();
+        bool ring_ok = got_ring.size() == N, blocked_ok = got_blocked.size() == N;
+        const uint64_t rows_per_rank = M / (uint64_t)world;
+        for (uint64_t x = 0; x < N && (ring_ok || blocked_ok); ++x) {
+            volatile float chain = 0.5f, total = 0.0f;
+            for (uint64_t y = 0; y < M; ++y) chain = chain + value(y, x);
+            for (int r = 0; r < world; ++r) {
+                volatile float part = r == 0 ? 0.5f : -0.0f;
+                for (uint64_t y = (uint64_t)r * rows_per_rank; y < (uint64_t)(r + 1) * rows_per_rank; ++y) part = part + value(y, x);
+                total = r == 0 ? part : total + part;
+            }
+            float c = chain, t = total;
+            ring_ok = ring_ok && std::memcmp(&got_ring[x], &c, 4) == 0;
+            blocked_ok = blocked_ok && std::memcmp(&got_blocked[x], &t, 4) == 0;
+        }
+        CHECK(ring_ok);
+        CHECK(blocked_ok);
+    }
+
     api.check(ctx, api.peer_table_close(ctx));
     api.check(ctx, api.comm_destroy(ctx));
     std::printf("rank %d: %d checks, %d failures\n", rank, checks, failures);
