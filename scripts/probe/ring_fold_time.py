@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Times mdim_fold_sharded_axis (k_fold_ring) and mdim_fold_sharded_axis_blocked (k_fold_xchg) at world = 1 — the fold kernels
-without peers — against the evaluator's strided fold of the same data: (rows, 262144) f32, rows = 1024 / 512 / 128 (what 1 / 2 / 8
+without peers — against collect() of the same fold (the planner's column walk, k_fold_cols; COLLECT_NO_FASTPATH would be the evaluator): (rows, 262144) f32, rows = 1024 / 512 / 128 (what 1 / 2 / 8
 ranks hold of config 4).  Successive launches walk through different blocks of a 1 GiB buffer, so nothing is re-read from L2."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -46,7 +46,8 @@ for rows in (1024, 512, 128):
         e1.record(stream)
         ctx.sync(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        print(f"rows {rows:5d} x {C_} f32  {name:12s} {ms:.4f} ms  {4 * rows * C_ / ms / 1e6:.0f} GB/s", flush=True)
+        label = name if name != "evaluator" else f"collect() -> {ctx.last_kernel()}"
+        print(f"rows {rows:5d} x {C_} f32  {label:26s} {ms:.4f} ms  {4 * rows * C_ / ms / 1e6:.0f} GB/s", flush=True)
     comm.fold_status()
     runs["evaluator"][0](); ctx.sync()
     for name in ("k_fold_ring", "k_fold_xchg"):
