@@ -46,7 +46,7 @@ def main():
     names = demangle(list(per))
     rows = []
     for (mangled, c), name in zip(per.items(), names):
-        name = re.sub(r"\(.*$", "", name).replace("mdim::", "").replace("void ", "")
+        name = re.sub(r"\(.*$", "", name.replace("(anonymous namespace)::", "")).replace("mdim::", "").replace("void ", "")
         rows.append((name, c))
 
     def pick(pred):
@@ -58,6 +58,8 @@ def main():
         ("config 3: gather `k_eval<SigGatherF32, u64 slots, V=4>` (LTC64B = the 64-byte L2 fetch flavour)", pick(lambda n: "SigGatherF32" in n and "4, 4, false, 1, 1" in n)),
         ("config 4: row folds `k_fold_rows<FAST>` (TMA bulk) and `k_fold_regs<L, FAST>`", pick(lambda n: n.startswith("k_fold_rows") or n.startswith("k_fold_regs<2,") or n.startswith("k_fold_regs<8,"))),
         ("sharded-axis fold: `k_fold_ring<S>` (TMA row tiles + peer-memory hand-off)", pick(lambda n: n.startswith("k_fold_ring") or "k_fold_ring" in n)),
+        ("column walk `k_fold_xchg<S, DT, OP, ROWS, EXCHANGE>`: f32 / u64 sums, without (`k_fold_cols`, last argument false) and with the in-kernel all-reduce",
+         pick(lambda n: "k_fold_xchg<unsigned int, 5, 0" in n or "k_fold_xchg<unsigned long, 4, 0" in n)),
         ("config 5 / 4b: pre-built rank-N signatures `k_eval<SigDiagMulAddCF32 / SigSubBcastF32, …, V=8>`", pick(lambda n: ("SigDiagMulAddCF32" in n or "SigSubBcastF32" in n) and "unsigned int, 8, 4, false" in n)),
     ]
     md = ["# Round 2 — SASS summary of `libmdim_b200.so` (sm_100a)", "",
@@ -73,8 +75,11 @@ def main():
     for _, c in rows:
         tot.update(c)
     md += ["## Whole library", "", "| " + " | ".join(KEYS) + " |", "|" + "---|" * len(KEYS), "| " + " | ".join(str(tot.get(k, 0)) for k in KEYS) + " |", ""]
-    hot_ffma = sum(c.get("FFMA", 0) for n, c in rows if ("SigMulAddCF32" in n or "SigDiagMulAddCF32" in n or "SigSubBcastF32" in n or n.startswith("k_fold")))
-    md.append(f"FFMA in the f32 hot kernels (MulAdd / DiagMulAdd / SubBcast signatures, folds): **{hot_ffma}**.")
+    hot_ffma = sum(c.get("FFMA", 0) for n, c in rows if ("SigMulAddCF32" in n or "SigDiagMulAddCF32" in n or "SigSubBcastF32" in n or n.startswith("k_fold_ring") or n.startswith("k_fold_xchg")))
+    div_ffma = sum(c.get("FFMA", 0) for n, c in rows if n.startswith("k_fold_rows") or n.startswith("k_fold_regs"))
+    md.append(f"FFMA in the f32 hot kernels without a division (MulAdd / DiagMulAdd / SubBcast signatures, the ring fold, the column walk): **{hot_ffma}**.")
+    md.append(f"FFMA in `k_fold_rows` / `k_fold_regs` (all variants together): {div_ffma} — every one inside the IEEE division sequence of the fused epilogue's `fold / c`")
+    md.append("(`__fdiv_rn`, Newton steps on the reciprocal: not a contraction of the expression's own multiply and add; the adds of the fold chain are `FADD`).")
     out = os.path.join(ROOT, "profiles", "r2_sass_summary.md")
     open(out, "w").write("\n".join(md) + "\n")
     print(out, len(rows), "kernels; hot FFMA:", hot_ffma)
