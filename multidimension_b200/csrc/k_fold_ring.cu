@@ -39,7 +39,7 @@ constexpr int kRingThreads = 96;        // warp 0: producer (one lane); warps 1-
 constexpr int kRingCons = 64;
 constexpr int kRingStageBytes = 32 * 1024;
 constexpr int kRingStages = 6;
-constexpr unsigned long long kSpinLimit = 20ull * 1000 * 1000;  // polls of a local line (~100 ns each): ~2 s
+constexpr unsigned long long kSpinLimit = 3ull * 1000 * 1000;  // polls of a local line (one L2 round trip each, ~0.7 us): ~2 s
 
 __device__ __forceinline__ uint32_t rsm(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void st_line(char* p, uint32_t a, uint32_t b, uint32_t flag) {

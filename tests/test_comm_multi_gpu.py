@@ -13,12 +13,20 @@ from helpers import assert_same_bits
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+_GPUS = None
+
+
 def _gpu_count():
-    try:
-        import torch
-        return torch.cuda.device_count()
-    except Exception:
-        return 0
+    """GPUs of the box, counted ONCE in a fresh subprocess: after an in-process test has initialised CUDA through the product
+    library, torch.cuda.device_count() in the same process was seen to answer 1 on a 2-GPU box (and skipped the tests below)."""
+    global _GPUS
+    if _GPUS is None:
+        try:
+            out = subprocess.run([sys.executable, "-c", "import torch; print(torch.cuda.device_count())"], capture_output=True, text=True, timeout=300).stdout
+            _GPUS = int(out.strip().splitlines()[-1])
+        except Exception:
+            _GPUS = 0
+    return _GPUS
 
 
 @pytest.mark.gpu
@@ -160,3 +168,20 @@ def test_blocked_fold_single_rank_is_the_sequential_fold():
         comm.fold_sharded_axis(st, rows, cols, P.Sub, npdt(0), blocked=True)  # no identity: the ring route serves SUB
     comm.close()
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("route", ["ring", "blocked"])
+def test_a_missing_peer_is_an_error_not_a_hung_gpu(route, tmp_path):
+    """Both fused fold kernels wait on peers inside the kernel; their spins are bounded: a rank that calls alone gets MDIM_ERR_NCCL
+    from mdim_fold_sharded_axis_status after ~2 s, the error word is cleared, and the communicator still shuts down cleanly."""
+    world = 2
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    rdv = str(tmp_path / "rendezvous")
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "multi", "timeout_worker.py"), str(r), str(world), rdv, route],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o[-3000:]}"
+    assert "gave up after" in outs[0]
