@@ -825,3 +825,21 @@ def fold_rows(v, I, J, op, init):
         row.each(lambda x: s.__setitem__(0, op(s[0], x)))
         return s[0]
     return v.rows(I, J).map(fold)
+
+
+def blocked_fold_over_sharded_axis(blocks, op, init, identity):
+    """The all-reduce route of a fold over the SHARDED (outermost) axis (last row), restated with numpy rows:
+    `blocks[r]` holds rank r's rows (2-D array, rows x columns) in index order.  Every rank folds ITS rows exactly as the reference
+    does — `let mut s = start; row.each(|x| s = op(s, x))`, sequential, index order (src/view.rs:617-622, 250-252) — rank 0 starting
+    from `init`, the others from the operator's `identity`; the partial results are then combined in RANK ORDER:
+        out = ((P_0 (op) P_1) (op) P_2) ... (op) P_{N-1}.
+    For an associative operator this IS the reference's result; a float sum is reassociated at the rank boundaries only."""
+    import numpy as np
+    total = None
+    for r, rows in enumerate(blocks):
+        rows = np.asarray(rows)
+        part = np.full(rows.shape[1], init if r == 0 else identity, dtype=rows.dtype)
+        for i in range(rows.shape[0]):
+            part = op(part, rows[i])
+        total = part if r == 0 else op(total, part)
+    return total
