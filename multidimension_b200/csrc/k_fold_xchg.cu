@@ -72,19 +72,25 @@ template <class S, int DT, int OP, int ROWS, bool EXCHANGE>
 __global__ void __launch_bounds__(kXThreads, EXCHANGE ? 4 : 6) k_fold_xchg(const __grid_constant__ FoldXchgArgs A) {
     constexpr int EPT = 32 / (int)sizeof(S);
     pdl_entry(!EXCHANGE && A.nowait != 0);  // the exchange form always waits for its predecessor in the stream
-    const uint64_t n_groups = (A.row_bytes + 31) / 32;  // 32-byte column groups (the last one may be half: row_bytes % 16 == 0)
+    const uint64_t gpr = (A.row_bytes + 31) / 32;  // 32-byte column groups per row (the last one may be half: row_bytes % 16 == 0)
+    const uint64_t n_groups = EXCHANGE ? gpr : gpr * A.n_batch;  // one-GPU form: n_batch independent (rows x columns) blocks, results back to back
     const uint64_t n_slices = (n_groups + kXThreads - 1) / kXThreads;
     for (uint64_t slice = blockIdx.x; slice < n_slices; slice += gridDim.x) {
         const uint64_t g = slice * kXThreads + threadIdx.x;
         if (g >= n_groups) continue;
-        const uint64_t b0 = g * 32;
+        uint64_t gc = g, bi = 0;  // column group within the row, batch index
+        if constexpr (!EXCHANGE) {
+            if (A.n_batch > 1) { bi = g / gpr; gc = g - bi * gpr; }
+        }
+        const uint64_t b0 = gc * 32;
+        const uint64_t o0 = bi * A.row_bytes + b0;  // byte offset of this thread's results in `out`
         const bool full = b0 + 32 <= A.row_bytes;  // else only the first 16 bytes exist
         const int n_lines = full ? 4 : 2;
         S acc[EPT];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) acc[e] = (S)A.start;
         // ---- this rank's rows, in order ------------------------------------------------------------------------------------
-        const char* p = (const char*)A.rows + b0;
+        const char* p = (const char*)A.rows + bi * A.batch_pitch_bytes + b0;
         uint64_t r = 0;
         // A rolling window of ROWS loads in flight per thread: row r is folded, then its registers are refilled with row r + ROWS
         // (a batch of loads followed by a batch of adds drains the memory pipeline between batches: 6.0 vs 6.9 TB/s).  The alignment
@@ -140,8 +146,8 @@ __global__ void __launch_bounds__(kXThreads, EXCHANGE ? 4 : 6) k_fold_xchg(const
         if constexpr (!EXCHANGE) {
             uint32_t ow[8];
             pack<S>(acc, ow);
-            st128((char*)A.out + b0, ow[0], ow[1], ow[2], ow[3], false);
-            if (full) st128((char*)A.out + b0 + 16, ow[4], ow[5], ow[6], ow[7], false);
+            st128((char*)A.out + o0, ow[0], ow[1], ow[2], ow[3], false);
+            if (full) st128((char*)A.out + o0 + 16, ow[4], ow[5], ow[6], ow[7], false);
             continue;
         }
         uint32_t w[8];
@@ -321,8 +327,9 @@ const char* launch_fold_cols(const FoldColsPlan& C, void* out, cudaStream_t stre
     memset(&A, 0, sizeof A);
     A.n_rows = C.n_rows; A.row_bytes = C.row_bytes; A.pitch_bytes = C.pitch_bytes;
     A.world = 1; A.start = C.init; A.rows = C.src; A.out = out; A.nowait = C.nowait;
-    A.wide = !(((uintptr_t)C.src & 31) || (C.pitch_bytes & 31));
-    const uint64_t n_groups = (C.row_bytes + 31) / 32, n_slices = (n_groups + kXThreads - 1) / kXThreads;
+    A.n_batch = C.n_batch ? C.n_batch : 1; A.batch_pitch_bytes = C.batch_pitch_bytes;
+    A.wide = !(((uintptr_t)C.src & 31) || (C.pitch_bytes & 31) || (A.n_batch > 1 && (C.batch_pitch_bytes & 31)));
+    const uint64_t n_groups = (C.row_bytes + 31) / 32 * A.n_batch, n_slices = (n_groups + kXThreads - 1) / kXThreads;
     const int grid = (int)std::min<uint64_t>(n_slices, 1u << 30);
     return launch_pdl(fn, dim3(grid), dim3(kXThreads), 0, stream, A) == cudaSuccess ? "k_fold_cols" : nullptr;
 }

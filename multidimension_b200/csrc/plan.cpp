@@ -686,22 +686,27 @@ int Builder::detect_fast_paths() {
     // (3) sequential fold over an OUTER axis of one leaf, the result contiguous (out stride 1): every output column is an independent
     //     chain down the rows and all addresses are known up front -> a column walk with 256-bit loads (k_fold_cols).  This is the
     //     one-GPU form of the fold over the sharded axis and each rank's partial fold of the all-reduce route.
-    if (fold_node >= 0 && root == fold_node && n_child[fold_node] == 1 && red_rank == 1 && rank == 1 && !(flags & kPlanScalarOut)) {
+    if (fold_node >= 0 && root == fold_node && n_child[fold_node] == 1 && red_rank == 1 && (rank == 1 || rank == 2) && !(flags & kPlanScalarOut)) {
+        // canonical axes: [batch,] columns, then the folded axis.  rank 2 = a fold over a MIDDLE axis: one column walk per outer coordinate
         const mdim_node& F = N[fold_node];
         const int fc = child[fold_node][0];
         const int es = dtype_size(F.dtype);
+        const int ac = rank - 1, ar = n_axes - 1;  // columns axis, folded axis
         const bool op_ok = F.op == MDIM_ADD || F.op == MDIM_SUB || F.op == MDIM_MUL || ((F.op == MDIM_AND || F.op == MDIM_OR || F.op == MDIM_XOR) && is_int(F.dtype));
-        if ((es == 4 || es == 8) && F.dtype != MDIM_U8 && op_ok && N[fc].kind == MDIM_NODE_LEAF && N[fc].dtype == F.dtype && N[fc].n_peers <= 1 && cstride[fc][0] == 1 &&
-            cstride[fc][1] >= (int64_t)len[0] && len[n_axes - 1] >= 1) {
-            const uint64_t row_bytes = len[0] * (uint64_t)es, pitch = (uint64_t)cstride[fc][1] * (uint64_t)es;
+        if ((es == 4 || es == 8) && F.dtype != MDIM_U8 && op_ok && N[fc].kind == MDIM_NODE_LEAF && N[fc].dtype == F.dtype && N[fc].n_peers <= 1 && cstride[fc][ac] == 1 &&
+            cstride[fc][ar] >= (int64_t)len[ac] && len[ar] >= 1 && (rank == 1 || cstride[fc][0] > 0)) {
+            const uint64_t row_bytes = len[ac] * (uint64_t)es, pitch = (uint64_t)cstride[fc][ar] * (uint64_t)es;
+            const uint64_t batch_pitch = rank == 2 ? (uint64_t)cstride[fc][0] * (uint64_t)es : 0;
             const uintptr_t base = (uintptr_t)N[fc].data + (uintptr_t)(N[fc].offset * es);
-            if (row_bytes % 16 == 0 && pitch % 16 == 0 && base % 16 == 0) {
+            if (row_bytes % 16 == 0 && pitch % 16 == 0 && batch_pitch % 16 == 0 && base % 16 == 0) {
                 FoldColsPlan& C = plan->fc;
                 memset(&C, 0, sizeof C);
-                C.src = (const void*)base; C.n_rows = len[n_axes - 1]; C.row_bytes = row_bytes; C.pitch_bytes = pitch;
+                C.src = (const void*)base; C.n_rows = len[ar]; C.row_bytes = row_bytes; C.pitch_bytes = pitch;
+                C.n_batch = rank == 2 ? len[0] : 1; C.batch_pitch_bytes = batch_pitch;
                 C.op = F.op; C.dtype = F.dtype; C.init = es == 4 ? (F.imm.u64 & 0xffffffffull) : F.imm.u64;
                 plan->kind = KK_FOLD_COLS;
-                snprintf(plan->describe, sizeof plan->describe, "fold_cols rows=%llu cols=%llu es%d op=%d", (unsigned long long)C.n_rows, (unsigned long long)len[0], es, C.op);
+                snprintf(plan->describe, sizeof plan->describe, "fold_cols batch=%llu rows=%llu cols=%llu es%d op=%d", (unsigned long long)C.n_batch, (unsigned long long)C.n_rows,
+                         (unsigned long long)len[ac], es, C.op);
                 return MDIM_OK;
             }
         }

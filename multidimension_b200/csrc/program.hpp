@@ -177,6 +177,8 @@ struct FoldColsPlan {
     uint64_t n_rows;      // reduction length: rows walked in index order
     uint64_t row_bytes;   // bytes of one row that take part (= bytes of the result; multiple of 16)
     uint64_t pitch_bytes; // bytes between consecutive rows (multiple of 16)
+    uint64_t n_batch;     // independent blocks (an axis OUTSIDE the folded one); their results lie back to back
+    uint64_t batch_pitch_bytes;  // bytes between consecutive blocks (multiple of 16)
     int32_t op, dtype;
     uint64_t init;
     int32_t nowait;       // set per launch (api.cu): see launch.cuh
@@ -208,6 +210,7 @@ struct FoldRingArgs {
 // compute + exchange kernel per GPU; flag-in-data packets through peer-mapped HBM, no fence, no NCCL call)
 struct FoldXchgArgs {
     uint64_t n_rows, row_bytes, pitch_bytes;  // this rank's rows; bytes of one row that take part (multiple of 16); bytes between rows
+    uint64_t n_batch, batch_pitch_bytes;      // one-GPU form only: independent (rows x columns) blocks and the bytes between them
     int32_t rank, world;
     uint32_t epoch;            // launch counter: the packets carry it, so the areas never need resetting
     int32_t wide;              // rows and pitch are 32-byte aligned: 256-bit loads

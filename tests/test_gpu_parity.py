@@ -270,6 +270,19 @@ def test_fold_over_outer_axis_column_walk(ctx):
     check(outer_fold(i32, 40, 12, Add, np.int32(-5)), ctx)     # wrapping
     d = Array.new((usize, usize), (33, 10), rng.uniform(0, 1, 330))
     check(outer_fold(d, 33, 10, Add, 0.5), ctx)
+    # a fold over a MIDDLE axis: one column walk per outer coordinate (batch), results back to back
+    for I, J, K in ((6, 10, 16), (3, 37, 8), (5, 2, 260), (2, 129, 4)):
+        t = Array.new((usize, usize, usize), (I, J, K), rng.uniform(0, 1, I * J * K).astype(np.float32))
+        v = fold_rows(t.transpose(usize, usize, usize, ()).iso(((usize, usize), usize)), (usize, usize), usize, Add, np.float32(0.5))
+        assert f"fold_cols batch={I} rows={J} cols={K}" in v.describe(), v.describe()
+        check(v, ctx)
+        check(v, ctx, F.COLLECT_NO_FASTPATH)
+        seq = np.full((I, K), np.float32(0.5))
+        for j in range(J):
+            seq = seq + t.as_ref().reshape(I, J, K)[:, j, :]
+        assert_same_bits(collect(v, ctx), seq.reshape(-1))
+    t64 = Array.new((usize, usize, usize), (4, 9, 6), rng.integers(0, 1 << 62, 216).astype(np.uint64), usize)
+    check(fold_rows(t64.transpose(usize, usize, usize, ()).iso(((usize, usize), usize)), (usize, usize), usize, BitXor, 0), ctx)
     # 17 columns: rows not a multiple of 16 bytes -> the evaluator keeps it
     odd = Array.new((usize, usize), (9, 17), rng.uniform(0, 1, 153).astype(np.float32))
     v = outer_fold(odd, 9, 17, Add, np.float32(0))
