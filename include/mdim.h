@@ -279,7 +279,9 @@ int mdim_peer_table_close(mdim_ctx* ctx);                                       
  * out[c] = (((init (op) x[0][c]) (op) x[1][c]) ... ) over ALL ranks' rows, on EVERY rank.  One fused kernel per GPU: the running
  * values travel rank to rank through peer-mapped HBM, pipelined over column slices (csrc/k_fold_ring.cu) — no all-reduce, no
  * reassociation.  op: MDIM_ADD, SUB, MUL, AND, OR, XOR; 4- and 8-byte dtypes; n_cols <= 2^20 per call, rows 16-byte aligned.
- * Asynchronous on the context's stream; mdim_fold_sharded_axis_status reports (and clears) a peer that never arrived. */
+ * Asynchronous on the context's stream; mdim_fold_sharded_axis_status reports (and clears) a peer that never arrived: the kernels' waits
+ * are bounded (~2 s), the result is then garbage, and the ranks' launch counters no longer agree — destroy and re-create the communicator
+ * on every rank before folding over a sharded axis again (tests/test_comm_multi_gpu.py::test_a_missing_peer_is_an_error_not_a_hung_gpu). */
 int mdim_fold_sharded_axis(mdim_ctx* ctx, const void* local_rows, uint64_t n_rows_local, uint64_t n_cols, int dtype, int op, mdim_scalar init,
                            void* out_device);
 int mdim_fold_sharded_axis_status(mdim_ctx* ctx);
