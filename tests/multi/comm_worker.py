@@ -93,6 +93,13 @@ def main():
         out["fold_blocked_i32_add"] = comm.fold_sharded_axis(i32.storage, ib, 4124, Add, np.int32(-7), blocked=True).to_numpy()
     comm.fold_status()
 
+    # wider than one packet area (two launches: the areas alternate) and a DIFFERENT number of rows on every rank
+    wide_cols, my_rows = (1 << 20) + 72, 3 + rank
+    wide_vals = np.random.default_rng([11, rank]).uniform(0, 1, my_rows * wide_cols).astype(np.float32)
+    wide = Array.new((usize, usize), (my_rows, wide_cols), wide_vals).to_device(ctx)
+    out["fold_blocked_wide_ragged"] = comm.fold_sharded_axis(wide.storage, my_rows, wide_cols, Add, np.float32(1.5), blocked=True).to_numpy()
+    comm.fold_status()
+
     # (5) all-reduce with the other operators / dtypes
     mine_vals = np.array([rank + 1, 10 - rank, 7], dtype=np.int64)
     for op in ("sum", "prod", "min", "max"):

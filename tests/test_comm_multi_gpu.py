@@ -10,6 +10,8 @@ import pytest
 
 from helpers import assert_same_bits
 
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -93,6 +95,12 @@ def test_c_abi_collectives_and_peer_tables(world, tmp_path):
         assert_same_bits(p["fold_blocked_f64_mul_init"], blocked64, "blocked fold (f64 mul, init 0.5)")
         assert_same_bits(p["fold_blocked_u64_xor"], want_xor, "blocked fold (u64 xor): associative, identical to the reference")
         assert_same_bits(p["fold_blocked_i32_add"], want_i32, "blocked fold (i32 wrapping add, rows 16-byte aligned only)")
+    wide_cols = (1 << 20) + 72
+    from reference_model import blocked_fold_over_sharded_axis
+    wide_blocks = [np.random.default_rng([11, r]).uniform(0, 1, (3 + r) * wide_cols).astype(np.float32).reshape(3 + r, wide_cols) for r in range(world)]
+    want_wide = blocked_fold_over_sharded_axis(wide_blocks, np.add, np.float32(1.5), np.float32(-0.0))
+    for p in parts:
+        assert_same_bits(p["fold_blocked_wide_ragged"], want_wide, "blocked fold: two packet-area windows, 3 + rank rows per rank")
     ranks = np.arange(world)
     for p in parts:
         assert p["ar_sum"].tolist() == [int((ranks + 1).sum()), int((10 - ranks).sum()), 7 * world]
