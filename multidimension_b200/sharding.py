@@ -17,6 +17,8 @@ Nothing here imports torch or torch.distributed: the collectives and the handle 
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import _ffi as F
@@ -100,6 +102,25 @@ class PeerStorage(Storage):
         self._opened = []
 
 
+def _prefer_bundled_nccl():
+    """Point the library at the NCCL wheel of this Python environment (`nvidia/nccl/lib/libnccl.so.2`, the copy torch links against)
+    unless the caller chose one (MDIM_NCCL_LIB).  The C library `dlopen`s "libnccl.so.2" by name, which finds the SYSTEM copy when torch has
+    not been imported yet; a later `import torch` in the same process would then bind libtorch_cuda.so to that older copy (one SONAME, one
+    mapping per process) and fail with an undefined symbol.  A C++ / Rust host has no torch: the system library is the right default there."""
+    import importlib.util
+    if os.environ.get("MDIM_NCCL_LIB"):
+        return
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for root in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(root, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["MDIM_NCCL_LIB"] = cand
+            return
+
+
 class Comm:
     """The communicator of the C ABI (`mdim_comm_*`, csrc/comm.cu): NCCL bound to a Context, one process per GPU.
     Every method is a collective call.  Nothing here touches torch.distributed: the data path of a sharded
@@ -108,6 +129,7 @@ class Comm:
     def __init__(self, ctx, rank, world, unique_id):
         import ctypes as C
         self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        _prefer_bundled_nccl()
         idb = (C.c_uint8 * F.COMM_ID_BYTES).from_buffer_copy(unique_id)
         ctx.check(ctx.lib.mdim_comm_init(ctx.handle, self.rank, self.world, idb))
         self._open = True
@@ -117,6 +139,7 @@ class Comm:
         """128 bytes made by rank 0 (ncclGetUniqueId); ship them to the other ranks by any means."""
         import ctypes as C
         idb = (C.c_uint8 * F.COMM_ID_BYTES)()
+        _prefer_bundled_nccl()
         st = F.lib().mdim_comm_unique_id(idb)
         if st != F.OK:
             raise F.MdimError(st, "mdim_comm_unique_id: " + F.lib().mdim_status_string(st).decode())
