@@ -24,9 +24,13 @@ def worker(rank, world, path):
     out = torch.empty(C_, device="cuda", dtype=torch.float32)
     so = Storage.wrap_device(ctx, F.F32, C_, out.data_ptr(), keep=out)
     torch.cuda.synchronize()
-    for rows in (8, 32, 128, 256, 512):
+    row_list = tuple(int(x) for x in os.environ.get("PROBE_ROWS", "8,32,128,256,512").split(","))
+    kernels = os.environ.get("PROBE_KERNELS", "xchg,ring").split(",")
+    for rows in row_list:
         n_blk = max(1, 512 // rows)
         for name, blocked in (("k_fold_xchg", True), ("k_fold_ring", False)):
+            if name.split("_")[-1] not in kernels:
+                continue
             fns = []
             for b in range(min(n_blk, 8)):
                 st = Storage.wrap_device(ctx, F.F32, rows * C_, big.data_ptr() + 4 * b * rows * C_, keep=big)
