@@ -93,8 +93,7 @@ __global__ void __launch_bounds__(kXThreads, EXCHANGE ? 4 : 6) k_fold_xchg(const
         const char* p = (const char*)A.rows + bi * A.batch_pitch_bytes + b0;
         uint64_t r = 0;
         // A rolling window of ROWS loads in flight per thread: row r is folded, then its registers are refilled with row r + ROWS
-        // (a batch of loads followed by a batch of adds drains the memory pipeline between batches: 6.0 vs 6.9 TB/s).  The alignment
-        // test is hoisted out of the loop.
+        // (ROWS = 12 measured best: profiles/r2_fold_cols_rows_in_flight.log).  The alignment test is hoisted out of the loop.
         auto walk = [&](auto wide_tag) {
             constexpr bool WIDE = decltype(wide_tag)::value;
             if (A.n_rows < (uint64_t)ROWS) return;  // short blocks: the row-at-a-time loop below
