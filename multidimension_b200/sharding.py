@@ -84,10 +84,11 @@ class PeerStorage(Storage):
     peer (the all-to-all of a row-sharded transpose, fused into the kernel); gathers (`compose`, `map_axis`)
     and every other chain pick the peer per element."""
 
-    def __init__(self, dtype, n, peers, block, keep=None, ctx=None, opened=()):
+    def __init__(self, dtype, n, peers, block, keep=None, ctx=None, opened=(), comm=None):
         super().__init__(dtype, n, dptr=peers[0], ctx=ctx, owns_device=False, keep=keep)
         self.peers = list(peers)
         self.block = int(block)
+        self.comm = comm   # with the communicator attached, collect() of a fold over the sharded axis runs the fused ring kernel (view.py)
         self.home = "device"
         self._opened = list(opened)
 
@@ -260,7 +261,7 @@ def peer_source(local_block_storage, total_len, comm):
     process (`mdim_peer_table`: CUDA IPC handles exchanged over the communicator) and return a PeerStorage
     addressing the whole source."""
     peers = comm.peer_table(local_block_storage.dptr, local_block_storage.nbytes)
-    return PeerStorage(local_block_storage.dtype, total_len, peers, equal_block(total_len, comm.world), keep=local_block_storage, ctx=comm.ctx)
+    return PeerStorage(local_block_storage.dtype, total_len, peers, equal_block(total_len, comm.world), keep=local_block_storage, ctx=comm.ctx, comm=comm)
 
 
 def all_gather_source(local_block, comm):

@@ -83,6 +83,13 @@ def main():
     out["fold_ring_u64_xor"] = comm.fold_sharded_axis(odd.storage, ib, 1028, P.BitXor, 0).to_numpy()
     comm.fold_status()
 
+    # (4a) collect() of the WHOLE fold over a peer-mapped Array that knows its communicator is routed to the same fused kernel by the planner rule
+    fp2 = PeerStorage(F.F32, I * J * K, fpeers.peers, ib * J * K, keep=A, ctx=ctx, comm=comm)
+    whole2 = Array((usize, usize, usize), (I, J, K), fp2, "f32")
+    auto = fold_rows(whole2.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize)), (usize, usize), usize, Add, np.float32(0)).collect(location="device", ctx=ctx)
+    out["fold_auto"] = auto.as_ref()
+    out["fold_auto_kernel"] = np.array([ord(c) for c in ctx.last_kernel()], dtype=np.uint8)
+
     # (4'') the all-reduce route as ONE fused kernel (k_fold_xchg): per-rank sequential partials combined in rank order
     out["fold_blocked"] = comm.fold_sharded_axis(A.storage, ib, J * K, Add, np.float32(0.125), blocked=True).to_numpy()
     out["fold_blocked_f64_mul_init"] = comm.fold_sharded_axis(A64.storage, ib, J * K, P.Mul, 0.5, blocked=True).to_numpy()

@@ -74,6 +74,8 @@ def test_c_abi_collectives_and_peer_tables(world, tmp_path):
         assert_same_bits(p["fold_ring"], seq, "ring fold over the sharded axis (f32 add)")
         assert_same_bits(p["fold_ring_f64_mul_init"], seq64, "ring fold (f64 mul, init 0.5)")
         assert_same_bits(p["fold_ring_u64_xor"], want_xor, "ring fold (u64 xor, ragged slice)")
+        assert_same_bits(p["fold_auto"], seq, "collect() of the whole fold over the sharded axis (planner rule -> fused kernel)")
+        assert bytes(p["fold_auto_kernel"]).decode() == "k_fold_ring"
     # the blocked route: P_r sequential (rank 0 from init, the others from the identity), combined in rank order — restated here
     rows = a.reshape(world, ib, J * K)
     blocked, blocked64 = None, None

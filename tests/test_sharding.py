@@ -332,3 +332,53 @@ def test_world2_gloo_peer_mapped_flows(tmp_path):
     assert_same_bits(np.concatenate([p["fo"] for p in parts]), seq)  # bit-exact: no reassociation across ranks
     idx = rng.integers(0, full.size, 3000).astype(np.uint64)
     assert_same_bits(np.concatenate([p["ga"] for p in parts]), full[idx.astype(np.int64)])
+
+
+def test_collect_routes_a_whole_fold_over_the_sharded_axis_to_the_fused_kernel():
+    """view.py::_fused_sharded_axis_fold — the planner rule that sends `rows().map(fold)` over the sharded axis of a whole peer-mapped
+    Array to `mdim_fold_sharded_axis` — matches exactly that shape and nothing else (host logic only: the communicator is a stand-in)."""
+    from multidimension_b200 import view as V
+
+    class FakeComm:
+        rank, world = 1, 2
+        calls = []
+
+        def __init__(self, ctx):
+            self.ctx = ctx
+
+        def fold_sharded_axis(self, local, rows, cols, op, init, out=None):
+            FakeComm.calls.append((local.dptr, local.n, rows, cols, op.code, init))
+            return "result"
+
+        def fold_status(self):
+            pass
+
+    ctx = object()
+    I, J, K = 8, 3, 4
+    data = np.zeros(I * J * K // 2, np.float32)
+    keep = [data, data.copy()]
+    comm = FakeComm(ctx)
+    st = PeerStorage(F.F32, I * J * K, [k.ctypes.data for k in keep], I * J * K // 2, keep=keep, comm=comm)
+    orig_wrap = V.Storage.wrap_device
+    V.Storage.wrap_device = staticmethod(lambda ctx_, dtype, n, ptr, keep=None: type("S", (), {"dptr": ptr, "n": n, "dtype": dtype})())
+    try:
+        whole = Array((usize, usize, usize), (I, J, K), st, "f32")
+        outer = fold_rows(whole.transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize)), (usize, usize), usize, Add, np.float32(0.5))
+
+        def route(view, flags=0):
+            groups, value = view._lower()
+            from multidimension_b200 import lowering as L
+            return V._fused_sharded_axis_fold(ctx, L.flatten_value(value), [a for g in groups for a in g], flags, None)
+        assert route(outer) == "result"
+        assert FakeComm.calls[-1] == (keep[1].ctypes.data, I * J * K // 2, I // 2, J * K, F.ADD, np.float32(0.5))   # THIS rank's block, its rows
+        assert route(outer, F.COLLECT_NO_FASTPATH) is None
+        assert route(shard_view(outer, 0, 2)) is None                                              # a block of the result: the peer-mapped evaluator
+        assert route(fold_rows(whole, (usize, usize), usize, Add, np.float32(0))) is None           # the LAST axis is local to every row
+        middle = fold_rows(whole.transpose(usize, usize, usize, ()).iso(((usize, usize), usize)), (usize, usize), usize, Add, np.float32(0))
+        assert route(middle) is None                                                                # a middle axis is not the sharded one
+        assert route(outer + outer) is None                                                         # anything around the fold
+        plain = PeerStorage(F.F32, I * J * K, [k.ctypes.data for k in keep], I * J * K // 2, keep=keep)
+        assert route(fold_rows(Array((usize, usize, usize), (I, J, K), plain, "f32").transpose((), (usize, usize), usize, ()).iso(((usize, usize), usize)),
+                               (usize, usize), usize, Add, np.float32(0))) is None                  # no communicator attached
+    finally:
+        V.Storage.wrap_device = orig_wrap
