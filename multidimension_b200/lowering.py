@@ -291,3 +291,106 @@ def emit(root, axes, location):
     em = Emitted(e, arr, order, root.dtype, out_len, bufs)
     em.out_dtypes = [c.dtype for c in root.children] if root.kind == F.TUPLE else [root.dtype]
     return em
+
+
+# ---- splitting an expression that does not fit ONE fused kernel -----------------------------------------------------------------
+# One mdim_expr is bounded (48 nodes, 56 instructions, 12 array operands, one FOLD: include/mdim.h).  The reference has no such
+# bound — a View chain is as long as the user writes it — so collect() falls back to SEVERAL kernels: sub-expressions are collected
+# into dense temporaries (over exactly the axes they depend on) and the rest of the tree reads them as ordinary Arrays.  Only nodes
+# that the fused kernel would evaluate UNCONDITIONALLY are cut out (the spine below the root through operators and gather
+# components); the inside of a Diagonal, of a Concat side and of a fold body stays in one piece, because the reference evaluates
+# those lazily (src/view.rs:846-857, 920-946) and a temporary would evaluate — and possibly panic — where the reference does not.
+_SPLIT_NODES, _SPLIT_OPERANDS = 20, 5    # a subtree beyond either is materialised: two such children + their parent stay under the limits
+
+
+def axes_used(node, memo=None):
+    """The position axes a value depends on (a fold's own reduction axes are internal to it)."""
+    memo = {} if memo is None else memo
+    if id(node) in memo:
+        return memo[id(node)]
+    used = set()
+    for c in node.children:
+        used |= axes_used(c, memo)
+    if node.kind in (F.LEAF, F.IOTA, F.GATHER):
+        used |= {a for a, s in node.stride.items() if s != 0}
+    if node.kind == F.DIAG:
+        for pr in node.pairs:
+            used.add(pr[0])
+            if not isinstance(pr[1], int):
+                used.add(pr[1])
+    if node.kind == F.CONCAT:
+        used.add(node.pairs[0][0])
+    if node.kind == F.FOLD:
+        used -= set(node.red_axes)
+    memo[id(node)] = used
+    return used
+
+
+def _tree_cost(node):
+    """(nodes, array operands, folds) of a subtree as emit() writes it (shared subtrees count per use)."""
+    n, ops, folds = 1, int(node.kind in (F.LEAF, F.GATHER)), int(node.kind == F.FOLD)
+    for c in node.children:
+        cn, co, cf = _tree_cost(c)
+        n, ops, folds = n + cn, ops + co, folds + cf
+    return n, ops, folds
+
+
+def split_for_limits(root, axes, materialise):
+    """-> a tree equivalent to `root` in which every sub-expression beyond the split budget, and every fold but one, has been replaced
+    by a LEAF over a dense temporary; `materialise(subtree, sub_axes) -> storage` collects one (row-major over `sub_axes`, the axes of
+    `axes` the subtree depends on, in order).  -> None when nothing could be cut (the expression is too large INSIDE a lazy region)."""
+    cut = [0]
+
+    def temp_leaf(node):
+        used = axes_used(node)
+        sub_axes = [a for a in axes if a in used]
+        if len(sub_axes) != len(used):
+            return None  # depends on an axis the root does not iterate (inside a fold body): not a spine node after all
+        storage = materialise(node, sub_axes)
+        stride, acc = {}, 1
+        for a in reversed(sub_axes):
+            stride[a] = acc
+            acc *= a.length
+        cut[0] += 1
+        return Node(F.LEAF, node.dtype, buf=storage, stride=stride)
+
+    def visit(node, is_root):
+        """-> (node', nodes, operands, folds) with every over-budget spine child already replaced."""
+        if node.kind == F.FOLD and len(node.children) == 2:  # a fold continued from a per-row initial VIEW (evaluated for every row): a fold in there runs first
+            init, in_n, in_ops, in_folds = visit(node.children[0], False)
+            if in_folds and init.kind not in (F.LEAF, F.CONST, F.IOTA):
+                leaf = temp_leaf(init)
+                if leaf is not None:
+                    node = node.clone(children=(leaf, node.children[1]))
+            elif init is not node.children[0]:
+                node = node.clone(children=(init, node.children[1]))
+            return (node,) + _tree_cost(node)
+        if node.kind not in (F.UNARY, F.BINARY, F.GATHER, F.TUPLE):  # a unit: leaf, constant, iota, or a lazy region / fold as a whole
+            return (node,) + _tree_cost(node)
+        kids, costs = [], []
+        folds = 0
+        for c in node.children:
+            c2, cn, co, cf = visit(c, False)
+            over = cn > _SPLIT_NODES or co > _SPLIT_OPERANDS or (cf and folds)   # too big, or a second fold under this node
+            if over and c2.kind not in (F.LEAF, F.CONST, F.IOTA):
+                leaf = temp_leaf(c2)
+                if leaf is not None:
+                    c2, cn, co, cf = leaf, 1, 1, 0
+            kids.append(c2)
+            costs.append([cn, co, cf])
+            folds += cf
+        own_ops = int(node.kind == F.GATHER)
+        while 1 + sum(c[0] for c in costs) > F.MAX_NODES - 4 or own_ops + sum(c[1] for c in costs) > 11:  # many children (gather components, a tuple)
+            k = max(range(len(kids)), key=lambda i: costs[i][0] if kids[i].kind not in (F.LEAF, F.CONST, F.IOTA) else -1)
+            if kids[k].kind in (F.LEAF, F.CONST, F.IOTA):
+                break
+            leaf = temp_leaf(kids[k])
+            if leaf is None:
+                break
+            kids[k], costs[k] = leaf, [1, 1, 0]
+        n, ops, folds = 1 + sum(c[0] for c in costs), own_ops + sum(c[1] for c in costs), sum(c[2] for c in costs)
+        out = node.clone(children=tuple(kids)) if any(a is not b for a, b in zip(kids, node.children)) else node
+        return out, n, ops, folds
+
+    new_root, _, _, _ = visit(root, True)
+    return new_root if cut[0] else None

@@ -294,14 +294,25 @@ class View:
         storages = []
         outs = list(out) if isinstance(out, (tuple, list)) else ([out] if out is not None else [None] * len(leaves_T))
         nodes = L.flatten_value(value)
-        fused = _fused_sharded_axis_fold(ctx, nodes, axes, flags, outs[0]) if len(nodes) == 1 and location != "host" else None
-        if fused is not None:
-            storages = [fused]
-        elif 1 < len(nodes) <= F.MAX_OUTS and all(_location_of(n, location) == "device" for n in nodes):
-            storages = _run_tuple(ctx, nodes, axes, flags, outs)  # ONE kernel launch: shared operands are read once
-        else:  # host-resident operands (mdim_collect_host is per leaf), or more leaves than one launch writes
-            for node, T, o in zip(nodes, leaves_T, outs):
-                storages.append(_run(ctx, node, axes, flags, location, o))
+
+        def run_all(nodes):
+            fused = _fused_sharded_axis_fold(ctx, nodes, axes, flags, outs[0]) if len(nodes) == 1 and location != "host" else None
+            if fused is not None:
+                return [fused]
+            if 1 < len(nodes) <= F.MAX_OUTS and all(_location_of(n, location) == "device" for n in nodes):
+                return _run_tuple(ctx, nodes, axes, flags, outs)  # ONE kernel launch: shared operands are read once
+            # host-resident operands (mdim_collect_host is per leaf), or more leaves than one launch writes
+            return [_run(ctx, node, axes, flags, location, o) for node, o in zip(nodes, outs)]
+        try:
+            storages = run_all(nodes)
+        except F.MdimError as e:
+            if e.status != F.ERR_UNSUPPORTED:
+                raise
+            # beyond what ONE fused kernel takes (nodes, instructions, operands, a second fold): several kernels through dense temporaries
+            split = [L.split_for_limits(n, axes, lambda sub, sub_axes: _run(ctx, sub, sub_axes, flags, location, None)) for n in nodes]
+            if all(n2 is None for n2 in split):
+                raise
+            storages = run_all([n2 if n2 is not None else n for n2, n in zip(split, nodes)])
         st = _build_like(self.T, list(storages)) if isinstance(self.T, tuple) else storages[0]
         return Array(I_out, size_out, st, self.T)
 

@@ -90,18 +90,32 @@ def emu_collect_tuple(view, flags=0):
     return _shape_result(view, _run_host_tuple(view, run))
 
 
-def _run_host(view, runner):
+def _run_host(view, runner, split=True):
+    """One descriptor per scalar leaf; an expression beyond what ONE fused kernel takes (MDIM_ERR_UNSUPPORTED: nodes, operands, a second
+    fold) is split through dense temporaries exactly as View.collect does (lowering.split_for_limits), unless split=False."""
     groups, value = view._lower()
     axes = _flat(groups)
-    outs = []
-    for node in L.flatten_value(value):
-        em = L.emit(node, axes, "host")
+
+    def run_node(node, node_axes):
+        em = L.emit(node, node_axes, "host")
         out = np.zeros(em.out_len, dtype=NP_OF[em.out_dtype])
         info = F.ErrorInfo()
         st = runner(em, out, info)
         if st != F.OK:
             raise CheckerPanic(st, info)
-        outs.append(out)
+        return out
+    outs = []
+    for node in L.flatten_value(value):
+        try:
+            outs.append(run_node(node, axes))
+        except (F.MdimError, CheckerPanic) as e:
+            if not split or e.status != F.ERR_UNSUPPORTED:
+                raise
+            from multidimension_b200.runtime import Storage
+            node2 = L.split_for_limits(node, axes, lambda sub, sub_axes: Storage.from_host(sub.dtype, run_node(sub, sub_axes)))
+            if node2 is None:
+                raise
+            outs.append(run_node(node2, axes))
     return outs
 
 
@@ -113,12 +127,12 @@ def _shape_result(view, outs):
     return outs[0]
 
 
-def oracle_collect(view):
+def oracle_collect(view, split=True):
     lib = oracle_lib()
-    return _shape_result(view, _run_host(view, lambda em, out, info: lib.mdim_oracle_collect(C.byref(em.expr), out.ctypes.data, C.byref(info))))
+    return _shape_result(view, _run_host(view, lambda em, out, info: lib.mdim_oracle_collect(C.byref(em.expr), out.ctypes.data, C.byref(info)), split))
 
 
-def emu_collect(view, flags=0, describe=None):
+def emu_collect(view, flags=0, describe=None, split=True):
     lib = emu_lib()
 
     def run(em, out, info):
@@ -127,7 +141,7 @@ def emu_collect(view, flags=0, describe=None):
         if describe is not None:
             describe.append(buf.value.decode())
         return st
-    return _shape_result(view, _run_host(view, run))
+    return _shape_result(view, _run_host(view, run, split))
 
 
 def as_list(x):

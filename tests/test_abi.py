@@ -173,7 +173,7 @@ def test_descriptor_limits_are_declined_cleanly():
     for k in range(12):
         many = many + Array.new(usize, 16, np.full(16, k, np.float32))
     with pytest.raises((P.MdimError, CheckerPanic)) as e:
-        emu_collect(many)
+        emu_collect(many, split=False)
     assert e.value.status == F.ERR_UNSUPPORTED
 
 
