@@ -312,7 +312,7 @@ def axes_used(node, memo=None):
     for c in node.children:
         used |= axes_used(c, memo)
     if node.kind in (F.LEAF, F.IOTA, F.GATHER):
-        used |= {a for a, s in node.stride.items() if s != 0}
+        used |= set(node.stride)  # zero strides too: emit() wants every named axis iterated
     if node.kind == F.DIAG:
         for pr in node.pairs:
             used.add(pr[0])
@@ -340,8 +340,11 @@ def split_for_limits(root, axes, materialise):
     by a LEAF over a dense temporary; `materialise(subtree, sub_axes) -> storage` collects one (row-major over `sub_axes`, the axes of
     `axes` the subtree depends on, in order).  -> None when nothing could be cut (the expression is too large INSIDE a lazy region)."""
     cut = [0]
+    temps, seen = {}, {}   # a sub-expression used several times (a traced closure mentioning its argument twice) is collected ONCE
 
     def temp_leaf(node):
+        if id(node) in temps:
+            return temps[id(node)]
         used = axes_used(node)
         sub_axes = [a for a in axes if a in used]
         if len(sub_axes) != len(used):
@@ -352,10 +355,16 @@ def split_for_limits(root, axes, materialise):
             stride[a] = acc
             acc *= a.length
         cut[0] += 1
-        return Node(F.LEAF, node.dtype, buf=storage, stride=stride)
+        temps[id(node)] = Node(F.LEAF, node.dtype, buf=storage, stride=stride)
+        return temps[id(node)]
 
     def visit(node, is_root):
         """-> (node', nodes, operands, folds) with every over-budget spine child already replaced."""
+        if id(node) not in seen:
+            seen[id(node)] = visit_once(node, is_root)
+        return seen[id(node)]
+
+    def visit_once(node, is_root):
         if node.kind == F.FOLD and len(node.children) == 2:  # a fold continued from a per-row initial VIEW (evaluated for every row): a fold in there runs first
             init, in_n, in_ops, in_folds = visit(node.children[0], False)
             if in_folds and init.kind not in (F.LEAF, F.CONST, F.IOTA):

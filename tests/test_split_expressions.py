@@ -107,3 +107,44 @@ def test_lazy_regions_are_never_cut(backend):
     for k in range(30):
         w = binary(w, Both(M.Scalar(k % 3), P.Scalar(k % 3, "i64"), "i64", "Scalar"), "Add")
     compare(w, product(w.p, backend), model_result(w), "long chain over a diagonal")
+
+
+def _long_chain(seed):
+    """test_differential_model.build_chain with 10-16 operations instead of 1-4, arithmetic-heavy: many of them exceed one expression."""
+    import test_differential_model as D
+    rng = random.Random(seed)
+    v = D.start_view(rng, "i64")   # integers: the model's unbounded ints reduced mod 2^64 ARE Rust's wrapping + - * (a ring homomorphism); floats would drown in inf / nan
+    applied = 0
+    for _ in range(60):
+        if applied >= 10 + seed % 7:
+            break
+        op = rng.choice(D.STRUCTURAL + D.ARITH * 6)
+        try:
+            w = op(rng, v)
+        except (D.Skip, P.Unsupported):
+            continue
+        if w.length() > 3000 or D.n_axes(w.I, w.size) > D.MAX_AXES or isinstance(w.T, tuple):
+            continue
+        v = w
+        applied += 1
+    return v
+
+
+def test_long_random_chains_against_the_reference_model(backend):
+    """40 long random chains (structure AND arithmetic): whatever does not fit one kernel is split, and the result is still the model's."""
+    ran = split = 0
+    for seed in range(40):
+        v = _long_chain(9000 + seed)
+        try:
+            big = n_nodes(v.p)
+            got = product(v.p, backend)
+        except Exception as e:
+            if getattr(e, "status", None) != F.ERR_UNSUPPORTED:
+                raise
+            continue  # declined loudly (e.g. an over-limit chain inside a lazy region)
+        want = np.array([((int(w) + (1 << 63)) % (1 << 64)) - (1 << 63) for w in model_result(v)], dtype=np.int64)
+        from helpers import assert_same_bits
+        assert_same_bits(np.asarray(got).reshape(-1), want, f"seed {9000 + seed}: {v.note[:200]}")
+        ran += 1
+        split += int(big[0] > F.MAX_NODES or big[1] > 12 or big[2] > 1)
+    assert ran >= 25 and split >= 15, (ran, split)   # the rest is declined loudly: > 8 axes, or the long part sits inside a Concat side / Diagonal
