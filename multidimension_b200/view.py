@@ -318,7 +318,8 @@ class View:
 
     def prepare(self, out=None, ctx=None, flags=0):
         """Lower once, run many times: returns a `Prepared` whose `run()` is a single C-ABI call (the lowering
-        and descriptor emission are not repeated).  Device-resident operands and scalar element types only."""
+        and descriptor emission are not repeated).  Device-resident operands and scalar element types only; ONE fused kernel:
+        an expression beyond its limits raises Unsupported here (collect() splits such an expression, lowering.split_for_limits)."""
         groups, value = self._lower()
         if isinstance(value, tuple):
             raise Unsupported("prepare() of a tuple-typed view: prepare the components")
